@@ -1,0 +1,109 @@
+"""ctypes binding of ``libesb200.so`` (C ABI declared in ``include/esb200.h``).
+
+The product path fails loudly when the CUDA library is missing: there is no CPU fallback.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libesb200.so')
+
+_CT = {'p': ctypes.c_void_p, 'q': ctypes.c_longlong, 'i': ctypes.c_int, 'f': ctypes.c_float, 'z': ctypes.c_size_t}
+
+# name -> (argument codes, return code).  p=pointer q=long long i=int f=float z=size_t
+SIGNATURES = {
+    'esb_last_error': ('', 'p'),
+    'esb_voxelize_points': ('pqiifpp', 'i'),
+    'esb_hash_capacity': ('q', 'q'),
+    'esb_coord_unique_workspace_bytes': ('q', 'z'),
+    'esb_coord_unique': ('pqippqppppzp', 'i'),
+    'esb_hash_build': ('pqppqp', 'i'),
+    'esb_hash_lookup': ('pqppqpp', 'i'),
+    'esb_kernel_map': ('pqpippqpp', 'i'),
+    'esb_kernel_map_transpose': ('piqqpp', 'i'),
+    'esb_kmap_pairs_workspace_bytes': ('iq', 'z'),
+    'esb_kmap_pairs': ('piqppppzp', 'i'),
+    'esb_generative_children': ('pqipp', 'i'),
+    'esb_spconv_fwd': ('ppppqiiiiiip', 'i'),
+    'esb_spconv_wgrad': ('ppppppqiiiip', 'i'),
+    'esb_maxpool_fwd': ('ppppqiiip', 'i'),
+    'esb_maxpool_bwd': ('pppqiip', 'i'),
+    'esb_norm_fwd': ('ppppiqiippfppfipppip', 'i'),
+    'esb_norm_apply': ('pppqippppipip', 'i'),
+    'esb_norm_bwd': ('pppppiqiipppippppip', 'i'),
+    'esb_act_fwd': ('ppqiip', 'i'),
+    'esb_paint_meta_bytes': ('', 'i'),
+    'esb_paint_fwd': ('pqfppipiiiffppip', 'i'),
+    'esb_paint_bwd': ('pqfppipiiiffpip', 'i'),
+    'esb_fcaf3d_targets_workspace_bytes': ('ii', 'z'),
+    'esb_fcaf3d_targets': ('ppiipppiiippppp' + 'zp', 'i'),
+    'esb_focal_loss_fwd': ('ppqiffpip', 'i'),
+    'esb_focal_loss_bwd': ('ppqiffppip', 'i'),
+    'esb_nms_bev_segmented': ('ppiifipp', 'i'),
+    'esb_iou_bev_pairwise': ('pipiipp', 'i'),
+    'esb_img_normalize': ('piiiiippiipip', 'i'),
+    'esb_unproject_depth_workspace_bytes': ('iii', 'z'),
+    'esb_unproject_depth': ('piiifpppppzp', 'i'),
+    'esb_grad_clip_coef': ('pqffpp', 'i'),
+    'esb_adamw_step': ('pppppqfffffifpp', 'i'),
+    'esb_cast_f32_to_bf16': ('ppqp', 'i'),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return list(SIGNATURES.keys())
+
+
+def lib():
+    """Load the library (once). Raises if it was not built — never falls back to a CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                '(esb200 has no CPU fallback)')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (args, ret) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = [_CT[c] for c in args]
+            fn.restype = _CT[ret]
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    p = lib().esb_last_error()
+    return ctypes.cast(p, ctypes.c_char_p).value.decode() if p else ''
+
+
+def ptr(t):
+    """Device (or host) pointer of a tensor, None -> NULL."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f'{name} failed ({rc}): {last_error()}')
+
+
+def query(name, *args):
+    return getattr(lib(), name)(*args)
+
+
+def dtype_code(dtype):
+    if dtype == torch.float32:
+        return 0
+    if dtype == torch.bfloat16:
+        return 1
+    raise TypeError(f'esb200 kernels take float32 or bfloat16 features, got {dtype}')

@@ -1,0 +1,295 @@
+// esb200 — row-feature operators around the sparse convolutions: strided max pooling, segmented
+// normalisation (BatchNorm over all rows = 1 segment, InstanceNorm = 1 segment per scan) fused with the
+// residual add and the activation. Replace ME.MinkowskiMaxPooling / MinkowskiInstanceNorm / MinkowskiBatchNorm /
+// MinkowskiReLU / MinkowskiELU (†upstream) as used at embodiedscan/models/backbones/mink_resnet.py:64-69 and
+// embodiedscan/models/dense_heads/fcaf3d_head.py:919-947. All HBM/L2-bound, vectorised along channels.
+#include "common.cuh"
+
+namespace {
+
+// ---------------- max pooling over a kernel map ----------------
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, const int* __restrict__ nbr, T* __restrict__ y,
+                                   int* __restrict__ arg, long long n_out, int C, int K) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_out * C) return;
+  long long o = t / C;
+  int c = (int)(t - o * C);
+  float best = -INFINITY;
+  int best_i = -1;
+  for (int k = 0; k < K; ++k) {
+    int i = nbr[(long long)k * n_out + o];
+    if (i < 0) continue;
+    float v = esb_to_float<T>(x[(long long)i * C + c]);
+    if (best_i < 0 || v > best) {
+      best = v;
+      best_i = i;
+    }
+  }
+  y[t] = esb_from_float<T>(best_i >= 0 ? best : 0.f);
+  arg[t] = best_i;
+}
+
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const int* __restrict__ arg, T* __restrict__ dx,
+                                   long long n_out, int C) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_out * C) return;
+  int c = (int)(t % C);
+  int i = arg[t];
+  // k2/s2 windows do not overlap: every (input row, channel) is the argmax of at most one output.
+  if (i >= 0) dx[(long long)i * C + c] = dy[t];
+}
+
+// ---------------- segmented column statistics ----------------
+// pass 1: sum over rows of each segment -> out[s][c]; pass 2 (centered): sum (x-mean)^2.
+template <typename T, int MODE>  // MODE 0: sum x ; 1: sum (x - mean[s][c])^2
+__global__ void seg_colstat_kernel(const T* __restrict__ x, const int* __restrict__ seg_off, const float* __restrict__ mean,
+                                   float* __restrict__ out, int C, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int s = blockIdx.y;
+  const int c = blockIdx.z * 32 + threadIdx.x;
+  const int r_beg = seg_off[s] + blockIdx.x * rows_per_block;
+  const int r_end = min(seg_off[s + 1], r_beg + rows_per_block);
+  float acc = 0.f;
+  if (c < C) {
+    float mu = MODE == 1 ? mean[s * C + c] : 0.f;
+    for (int r = r_beg + threadIdx.y; r < r_end; r += 8) {
+      float v = esb_to_float<T>(x[(long long)r * C + c]);
+      if (MODE == 1) {
+        v -= mu;
+        acc = fmaf(v, v, acc);
+      } else {
+        acc += v;
+      }
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C && r_beg < r_end) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    atomicAdd(&out[s * C + c], t);
+  }
+}
+
+// mean = sum / n ; (in place)
+__global__ void seg_finalize_mean_kernel(float* __restrict__ sum, const int* __restrict__ seg_off, int S, int C) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S * C) return;
+  int s = t / C;
+  int n = seg_off[s + 1] - seg_off[s];
+  sum[t] = n > 0 ? sum[t] / (float)n : 0.f;
+}
+// var(biased) -> rstd ; optionally update running stats (momentum, unbiased var) like nn.BatchNorm1d
+__global__ void seg_finalize_rstd_kernel(const float* __restrict__ mean, float* __restrict__ var_to_rstd,
+                                         const int* __restrict__ seg_off, int S, int C, float eps,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         float momentum) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S * C) return;
+  int s = t / C;
+  int n = seg_off[s + 1] - seg_off[s];
+  float var = n > 0 ? var_to_rstd[t] / (float)n : 0.f;
+  if (running_mean != nullptr && S == 1) {
+    float unbiased = n > 1 ? var * (float)n / (float)(n - 1) : var;
+    running_mean[t] = (1.f - momentum) * running_mean[t] + momentum * mean[t];
+    running_var[t] = (1.f - momentum) * running_var[t] + momentum * unbiased;
+  }
+  var_to_rstd[t] = rsqrtf(var + eps);
+}
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == 1) return fmaxf(z, 0.f);
+  if (act == 2) return z > 0.f ? z : expm1f(z);
+  return z;
+}
+// derivative of the activation expressed through its OUTPUT y
+__device__ __forceinline__ float act_bwd_from_out(float y, int act) {
+  if (act == 1) return y > 0.f ? 1.f : 0.f;
+  if (act == 2) return y > 0.f ? 1.f : y + 1.f;
+  return 1.f;
+}
+
+// y = act((x - mean) * rstd * gamma + beta + res)
+template <typename T>
+__global__ void norm_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const int* __restrict__ row_seg,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
+                                  long long N, int C, int act) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= N * C) return;
+  long long r = t / C;
+  int c = (int)(t - r * C);
+  int s = row_seg ? row_seg[r] : 0;
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  float z = (esb_to_float<T>(x[t]) - mean[s * C + c]) * rstd[s * C + c] * g + b;
+  if (res) z += esb_to_float<T>(res[t]);
+  y[t] = esb_from_float<T>(act_fwd(z, act));
+}
+
+// backward reduce: sg[s][c] = sum g ; sgx[s][c] = sum g * xhat, with g = dy * act'(y)
+template <typename T>
+__global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                       const int* __restrict__ seg_off, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, float* __restrict__ sg, float* __restrict__ sgx,
+                                       int C, int rows_per_block, int act) {
+  __shared__ float red0[8][33];
+  __shared__ float red1[8][33];
+  const int s = blockIdx.y;
+  const int c = blockIdx.z * 32 + threadIdx.x;
+  const int r_beg = seg_off[s] + blockIdx.x * rows_per_block;
+  const int r_end = min(seg_off[s + 1], r_beg + rows_per_block);
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    float mu = mean[s * C + c], rs = rstd[s * C + c];
+    for (int r = r_beg + threadIdx.y; r < r_end; r += 8) {
+      long long idx = (long long)r * C + c;
+      float g = esb_to_float<T>(dy[idx]) * act_bwd_from_out(esb_to_float<T>(y[idx]), act);
+      float xh = (esb_to_float<T>(x[idx]) - mu) * rs;
+      a0 += g;
+      a1 = fmaf(g, xh, a1);
+    }
+  }
+  red0[threadIdx.y][threadIdx.x] = a0;
+  red1[threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C && r_beg < r_end) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      t0 += red0[j][threadIdx.x];
+      t1 += red1[j][threadIdx.x];
+    }
+    atomicAdd(&sg[s * C + c], t0);
+    atomicAdd(&sgx[s * C + c], t1);
+  }
+}
+
+// dx = gamma*rstd*(g - mean_s(g) - xhat*mean_s(g*xhat)) ; dres = g
+template <typename T>
+__global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                      const int* __restrict__ row_seg, const int* __restrict__ seg_off,
+                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                      const float* __restrict__ gamma, const float* __restrict__ sg,
+                                      const float* __restrict__ sgx, T* __restrict__ dx, T* __restrict__ dres,
+                                      long long N, int C, int act) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= N * C) return;
+  long long r = t / C;
+  int c = (int)(t - r * C);
+  int s = row_seg ? row_seg[r] : 0;
+  float inv_n = 1.f / (float)max(seg_off[s + 1] - seg_off[s], 1);
+  float g = esb_to_float<T>(dy[t]) * act_bwd_from_out(esb_to_float<T>(y[t]), act);
+  float rs = rstd[s * C + c];
+  float xh = (esb_to_float<T>(x[t]) - mean[s * C + c]) * rs;
+  float gm = gamma ? gamma[c] : 1.f;
+  float v = gm * rs * (g - sg[s * C + c] * inv_n - xh * sgx[s * C + c] * inv_n);
+  dx[t] = esb_from_float<T>(v);
+  if (dres) dres[t] = esb_from_float<T>(g);
+}
+
+// plain activation (used where no normalisation precedes it)
+template <typename T>
+__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int act) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < n) y[t] = esb_from_float<T>(act_fwd(esb_to_float<T>(x[t]), act));
+}
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)                         \
+  if (dtype == ESB_F32) {                              \
+    using T = float;                                   \
+    __VA_ARGS__;                                       \
+  } else {                                             \
+    using T = __nv_bfloat16;                           \
+    __VA_ARGS__;                                       \
+  }
+
+extern "C" int esb_maxpool_fwd(const void* x, const int* nbr, void* y, int* arg, long long n_out, int C, int K,
+                               int dtype, void* stream) {
+  if (n_out == 0) return ESB_OK;
+  DISPATCH_T(dtype, (maxpool_fwd_kernel<T><<<esb_div_up(n_out * C, 256), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, nbr, (T*)y, arg, n_out, C, K)));
+  ESB_CUDA_LAUNCH_CHECK("maxpool_fwd_kernel");
+  return ESB_OK;
+}
+
+// dx must be zero-initialised by the caller.
+extern "C" int esb_maxpool_bwd(const void* dy, const int* arg, void* dx, long long n_out, int C, int dtype,
+                               void* stream) {
+  if (n_out == 0) return ESB_OK;
+  DISPATCH_T(dtype, (maxpool_bwd_kernel<T><<<esb_div_up(n_out * C, 256), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dy, arg, (T*)dx, n_out, C)));
+  ESB_CUDA_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return ESB_OK;
+}
+
+// Segmented normalisation forward.
+//  seg_off (S+1) device int32 row offsets (rows of a segment are contiguous); row_seg (N) segment id per row or NULL
+//  when S==1. mean/rstd (S,C) fp32 outputs (saved for backward). gamma/beta may be NULL. res may be NULL.
+//  running_mean/var (C) updated when non-NULL and S==1 (BatchNorm training semantics, unbiased running var).
+extern "C" int esb_norm_fwd(const void* x, const void* res, const int* seg_off, const int* row_seg, int S,
+                            long long N, int max_seg_rows, int C, const float* gamma, const float* beta, float eps,
+                            float* running_mean, float* running_var, float momentum, int act, float* mean, float* rstd,
+                            void* y, int dtype, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESB_CHECK_ARG(S >= 1 && C >= 1, "esb_norm_fwd: bad S/C");
+  ESB_CUDA_CALL(cudaMemsetAsync(mean, 0, sizeof(float) * S * C, stream));
+  ESB_CUDA_CALL(cudaMemsetAsync(rstd, 0, sizeof(float) * S * C, stream));
+  if (N == 0) return ESB_OK;
+  const int rpb = 256;
+  dim3 grid(esb_div_up(max_seg_rows > 0 ? max_seg_rows : 1, rpb), S, esb_div_up(C, 32)), block(32, 8);
+  int fin = esb_div_up(S * C, 256);
+  DISPATCH_T(dtype, {
+    seg_colstat_kernel<T, 0><<<grid, block, 0, stream>>>((const T*)x, seg_off, nullptr, mean, C, rpb);
+    seg_finalize_mean_kernel<<<fin, 256, 0, stream>>>(mean, seg_off, S, C);
+    seg_colstat_kernel<T, 1><<<grid, block, 0, stream>>>((const T*)x, seg_off, mean, rstd, C, rpb);
+    seg_finalize_rstd_kernel<<<fin, 256, 0, stream>>>(mean, rstd, seg_off, S, C, eps, running_mean, running_var, momentum);
+    norm_apply_kernel<T><<<esb_div_up(N * C, 256), 256, 0, stream>>>((const T*)x, (const T*)res, row_seg, mean, rstd,
+                                                                     gamma, beta, (T*)y, N, C, act);
+  });
+  ESB_CUDA_LAUNCH_CHECK("esb_norm_fwd");
+  return ESB_OK;
+}
+
+// Inference-mode normalisation with given statistics (BatchNorm eval): mean/rstd (1,C) supplied by the caller.
+extern "C" int esb_norm_apply(const void* x, const void* res, const int* row_seg, long long N, int C,
+                              const float* mean, const float* rstd, const float* gamma, const float* beta, int act,
+                              void* y, int dtype, void* stream) {
+  if (N == 0) return ESB_OK;
+  DISPATCH_T(dtype, (norm_apply_kernel<T><<<esb_div_up(N * C, 256), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (const T*)res, row_seg, mean, rstd, gamma, beta, (T*)y, N, C, act)));
+  ESB_CUDA_LAUNCH_CHECK("norm_apply_kernel");
+  return ESB_OK;
+}
+
+// Backward: dgamma = sgx summed over segments, dbeta = sg summed over segments (the host sums the (S,C) arrays).
+extern "C" int esb_norm_bwd(const void* x, const void* y, const void* dy, const int* seg_off, const int* row_seg, int S,
+                            long long N, int max_seg_rows, int C, const float* mean, const float* rstd,
+                            const float* gamma, int act, float* sg, float* sgx, void* dx, void* dres, int dtype,
+                            void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESB_CUDA_CALL(cudaMemsetAsync(sg, 0, sizeof(float) * S * C, stream));
+  ESB_CUDA_CALL(cudaMemsetAsync(sgx, 0, sizeof(float) * S * C, stream));
+  if (N == 0) return ESB_OK;
+  const int rpb = 256;
+  dim3 grid(esb_div_up(max_seg_rows > 0 ? max_seg_rows : 1, rpb), S, esb_div_up(C, 32)), block(32, 8);
+  DISPATCH_T(dtype, {
+    norm_bwd_reduce_kernel<T><<<grid, block, 0, stream>>>((const T*)x, (const T*)y, (const T*)dy, seg_off, mean, rstd,
+                                                          sg, sgx, C, rpb, act);
+    norm_bwd_apply_kernel<T><<<esb_div_up(N * C, 256), 256, 0, stream>>>(
+        (const T*)x, (const T*)y, (const T*)dy, row_seg, seg_off, mean, rstd, gamma, sg, sgx, (T*)dx, (T*)dres, N, C, act);
+  });
+  ESB_CUDA_LAUNCH_CHECK("esb_norm_bwd");
+  return ESB_OK;
+}
+
+extern "C" int esb_act_fwd(const void* x, void* y, long long n, int act, int dtype, void* stream) {
+  if (n == 0) return ESB_OK;
+  DISPATCH_T(dtype, (act_fwd_kernel<T><<<esb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n, act)));
+  ESB_CUDA_LAUNCH_CHECK("act_fwd_kernel");
+  return ESB_OK;
+}

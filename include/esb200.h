@@ -1,0 +1,121 @@
+/* esb200.h — C ABI of libesb200.so, the sm_100a kernel library behind the EmbodiedScan hot path.
+ *
+ * The reference (OpenRobotLab/EmbodiedScan) has no FFI of its own: its kernels live in MinkowskiEngine, mmcv._ext and
+ * pytorch3d._C. Each entry point below names the reference call site / upstream operator it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host.
+ *  - the caller owns every buffer (inputs, outputs, workspace); the library never allocates device memory and
+ *    keeps no mutable global state. `*_workspace_bytes` returns the scratch size of the paired call.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no implicit synchronisation.
+ *    Data-dependent output sizes are written to a device int32 the caller reads after synchronising.
+ *  - return 0 on success, negative ESB_E* otherwise; esb_last_error() gives a thread-local message.
+ *  - dtype: 0 = fp32, 1 = bf16 (feature storage; accumulation is always fp32).
+ *  - coordinates are int32 (N,4) rows [batch, x, y, z]; |x|,|y|,|z| < 32768, batch < 65535.
+ */
+#ifndef ESB200_H
+#define ESB200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESB_OK 0
+#define ESB_EINVAL (-1)
+#define ESB_ECUDA (-2)
+#define ESB_ENOMEM (-3)
+#define ESB_ERANGE (-4)
+#define ESB_F32 0
+#define ESB_BF16 1
+
+const char* esb_last_error(void);
+
+/* ---- voxelisation hashing / coordinate maps -------------------------------------------------------------
+ * ME.utils.batch_sparse_collate + ME.SparseTensor(coordinates=, features=) at
+ * embodiedscan/models/detectors/sparse_featfusion_single_stage.py:109-118 ; CoordinateManager stride / kernel-map
+ * construction inside every ME.MinkowskiConvolution / MaxPooling / GenerativeConvolutionTranspose used by
+ * embodiedscan/models/backbones/mink_resnet.py:58-69,104-108 and embodiedscan/models/dense_heads/fcaf3d_head.py:919-946. */
+int esb_voxelize_points(const float* points, long long n, int pstride, int batch, float inv_voxel, int* coords,
+                        void* stream);
+long long esb_hash_capacity(long long n);
+size_t esb_coord_unique_workspace_bytes(long long n);
+int esb_coord_unique(const int* coords_in, long long n, int div, unsigned long long* keys, int* vals, long long cap,
+                     int* out_coords, int* in2out, int* count_dev, void* ws, size_t ws_bytes, void* stream);
+int esb_hash_build(const int* coords, long long n, unsigned long long* keys, int* vals, long long cap, void* stream);
+int esb_hash_lookup(const int* query, long long nq, const unsigned long long* keys, const int* vals, long long cap,
+                    int* out, void* stream);
+int esb_kernel_map(const int* out_coords, long long n_out, const int* offsets_host, int K,
+                   const unsigned long long* keys, const int* vals, long long cap, int* nbr, void* stream);
+int esb_kernel_map_transpose(const int* nbr_out, int K, long long n_out, long long n_in, int* nbr_in, void* stream);
+size_t esb_kmap_pairs_workspace_bytes(int K, long long n_out);
+int esb_kmap_pairs(const int* nbr, int K, long long n_out, int* pair_in, int* pair_out, int* k_offsets, void* ws,
+                   size_t ws_bytes, void* stream);
+int esb_generative_children(const int* coords_in, long long n_in, int half_stride, int* out_coords, void* stream);
+
+/* ---- sparse convolution (ME.MinkowskiConvolution fwd/bwd; mink_resnet.py:58-62, fcaf3d_head.py:919-946) -------- */
+int esb_spconv_fwd(const void* x, const void* w, const int* nbr, void* y, long long n_out, int cin, int cout, int K,
+                   int w_transposed, int accumulate, int dtype, void* stream);
+int esb_spconv_wgrad(const void* x, const void* dy, const int* pair_in, const int* pair_out, const int* k_offsets,
+                     float* dw, long long n_pairs_hint, int cin, int cout, int K, int dtype, void* stream);
+
+/* ---- pooling / normalisation / activation (ME.MinkowskiMaxPooling, InstanceNorm, BatchNorm, ReLU, ELU;
+ * mink_resnet.py:64-69, fcaf3d_head.py:923,942,947) -------------------------------------------------------------- */
+int esb_maxpool_fwd(const void* x, const int* nbr, void* y, int* arg, long long n_out, int C, int K, int dtype,
+                    void* stream);
+int esb_maxpool_bwd(const void* dy, const int* arg, void* dx, long long n_out, int C, int dtype, void* stream);
+int esb_norm_fwd(const void* x, const void* res, const int* seg_off, const int* row_seg, int S, long long N,
+                 int max_seg_rows, int C, const float* gamma, const float* beta, float eps, float* running_mean,
+                 float* running_var, float momentum, int act, float* mean, float* rstd, void* y, int dtype,
+                 void* stream);
+int esb_norm_apply(const void* x, const void* res, const int* row_seg, long long N, int C, const float* mean,
+                   const float* rstd, const float* gamma, const float* beta, int act, void* y, int dtype, void* stream);
+int esb_norm_bwd(const void* x, const void* y, const void* dy, const int* seg_off, const int* row_seg, int S,
+                 long long N, int max_seg_rows, int C, const float* mean, const float* rstd, const float* gamma, int act,
+                 float* sg, float* sgx, void* dx, void* dres, int dtype, void* stream);
+int esb_act_fwd(const void* x, void* y, long long n, int act, int dtype, void* stream);
+
+/* ---- point painting (batch_point_sample + apply_3d_transformation + batch_points_cam2img + F.grid_sample;
+ * embodiedscan/models/layers/fusion_layers/point_fusion.py:208-311, structures/bbox_3d/utils.py:289-332) -------- */
+int esb_paint_meta_bytes(void);
+int esb_paint_fwd(const int* coords, long long N, float voxel_size, const void* metas, const float* proj, int V,
+                  const void* feat, int Hf, int Wf, int C, float pad_h, float pad_w, void* out, int* valid_count,
+                  int dtype, void* stream);
+int esb_paint_bwd(const int* coords, long long N, float voxel_size, const void* metas, const float* proj, int V,
+                  const void* dout, int Hf, int Wf, int C, float pad_h, float pad_w, float* dfeat, int dtype,
+                  void* stream);
+
+/* ---- FCAF3D head: target assignment (fcaf3d_head.py:1578-1664) and sigmoid focal loss (mmcv.ops.sigmoid_focal_loss
+ * through mmdet.FocalLoss, cfg :46-52) --------------------------------------------------------------------------- */
+size_t esb_fcaf3d_targets_workspace_bytes(int L, int Ng);
+int esb_fcaf3d_targets(const float* points, const int* level_off, int L, int Np, const float* boxes, const float* rneg,
+                       const long long* labels, int Ng, int assign_thr, int center_thr, float* center_t, float* bbox_t,
+                       long long* cls_t, int* box_idx, void* ws, size_t ws_bytes, void* stream);
+int esb_focal_loss_fwd(const void* logits, const long long* target, long long n, int C, float gamma, float alpha,
+                       float* loss_sum, int dtype, void* stream);
+int esb_focal_loss_bwd(const void* logits, const long long* target, long long n, int C, float gamma, float alpha,
+                       const float* scale_dev, void* grad, int dtype, void* stream);
+
+/* ---- rotated BEV IoU + NMS (mmcv.ops.nms3d / nms3d_normal; fcaf3d_head.py:1666-1725) ---------------------------- */
+int esb_nms_bev_segmented(const float* boxes, const int* seg_off, int S, int max_seg, float iou_thr, int rotated,
+                          unsigned char* keep, void* stream);
+int esb_iou_bev_pairwise(const float* a, int na, const float* b, int nb, int rotated, float* out, void* stream);
+
+/* ---- input side: Det3DDataPreprocessor image path (data_preprocessor.py:249-264, utils.py:9-63) and the
+ * depth->points unprojection (datasets/transforms/points.py:30-81, multiview.py:139-169) ------------------------- */
+int esb_img_normalize(const unsigned char* src, int n_img, int H, int W, int Hp, int Wp, const float* mean3_host,
+                      const float* std3_host, int bgr_to_rgb, int channels_last, void* dst, int dtype, void* stream);
+size_t esb_unproject_depth_workspace_bytes(int V, int H, int W);
+int esb_unproject_depth(const unsigned short* depth, int V, int H, int W, float depth_shift, const float* mats,
+                        float* out, int* view_of, int* count_dev, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- optimiser step over the flat parameter arena (AdamW + clip_grad; cfg :219-223) ----------------------------- */
+int esb_grad_clip_coef(const float* grad, long long n, float max_norm, float world_scale, float* state, void* stream);
+int esb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* lr_mult,
+                   long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   float grad_scale, const float* clip_state, void* stream);
+int esb_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESB200_H */
