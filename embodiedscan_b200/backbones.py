@@ -1,0 +1,241 @@
+"""Backbones of the hot path, registered under the reference's names.
+
+* ``MinkResNet`` — sparse 3D ResNet (embodiedscan/models/backbones/mink_resnet.py:20-140) over ``esb200.sparse``.
+  Depth 14 = (BasicBlock, (1,1,1,1)) is added for BASELINE.json config C1.
+* ``ResNet`` (registered as ``mmdet.ResNet``) — the per-view 2D backbone named by the config
+  (configs/detection/mv-det3d_8xb4_embodiedscan-3d-284class-9dof.py:24-34): pytorch-style ResNet with
+  ``base_channels``, ``frozen_stages`` and ``norm_eval``. The BatchNorms are frozen (requires_grad=False, eval), so each
+  conv+BN pair is evaluated as ONE convolution with folded scale/shift, in channels-last bf16/fp32; the dense
+  contraction itself is the library conv (cuDNN) in this round — see DESIGN.md "2D backbone".
+"""
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import sparse as SP
+from .registry import MODELS
+
+
+@MODELS.register_module()
+class MinkResNet(nn.Module):
+    arch_settings = {
+        14: (SP.BasicBlock, (1, 1, 1, 1)),
+        18: (SP.BasicBlock, (2, 2, 2, 2)),
+        34: (SP.BasicBlock, (3, 4, 6, 3)),
+        50: (SP.Bottleneck, (3, 4, 6, 3)),
+        101: (SP.Bottleneck, (3, 4, 23, 3)),
+        152: (SP.Bottleneck, (3, 8, 36, 3)),
+    }
+
+    def __init__(self, depth: int, in_channels: int, num_stages: int = 4, pool: bool = True):
+        super().__init__()
+        if depth not in self.arch_settings:
+            raise KeyError(f'invalid depth {depth} for resnet')
+        assert 4 >= num_stages >= 1
+        block, stage_blocks = self.arch_settings[depth]
+        stage_blocks = stage_blocks[:num_stages]
+        self.num_stages, self.pool = num_stages, pool
+        self.inplanes = 64
+        self.conv1 = SP.MinkowskiConvolution(in_channels, self.inplanes, kernel_size=3, stride=2, dimension=3)
+        self.norm1 = SP.MinkowskiInstanceNorm(self.inplanes)
+        self.relu = SP.MinkowskiReLU(inplace=True)
+        if self.pool:
+            self.maxpool = SP.MinkowskiMaxPooling(kernel_size=2, stride=2, dimension=3)
+        for i in range(len(stage_blocks)):
+            setattr(self, f'layer{i + 1}', self._make_layer(block, 64 * 2 ** i, stage_blocks[i], stride=2))
+        self.init_weights()
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, SP.MinkowskiConvolution):
+                SP.kaiming_normal_(m.kernel, mode='fan_out', nonlinearity='relu')
+            if isinstance(m, SP.MinkowskiBatchNorm):
+                nn.init.constant_(m.bn.weight, 1)
+                nn.init.constant_(m.bn.bias, 0)
+
+    def _make_layer(self, block, planes, blocks, stride):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(
+                SP.MinkowskiConvolution(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride,
+                                        dimension=3), SP.MinkowskiBatchNorm(planes * block.expansion))
+        layers = [block(self.inplanes, planes, stride=stride, downsample=downsample, dimension=3)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes, stride=1, dimension=3))
+        return nn.Sequential(*layers)
+
+    def forward(self, x: SP.SparseTensor) -> List[SP.SparseTensor]:
+        x = self.conv1(x)
+        x = self.norm1(x, act=SP.ACT_RELU)      # InstanceNorm + ReLU fused
+        if self.pool:
+            x = self.maxpool(x)
+        outs = []
+        for i in range(self.num_stages):
+            x = getattr(self, f'layer{i + 1}')(x)
+            outs.append(x)
+        return outs
+
+
+# ------------------------------------------------------------------------------------------------------------
+# 2D ResNet (mmdet.ResNet semantics)
+# ------------------------------------------------------------------------------------------------------------
+def _fold(conv_w, bn: nn.BatchNorm2d, dtype):
+    scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    w = conv_w * scale[:, None, None, None]
+    b = bn.bias - bn.running_mean * scale
+    return w.to(dtype), b.to(dtype)
+
+
+class _ConvBN(nn.Module):
+    """Conv2d(bias=False) followed by a BatchNorm2d; evaluated folded when the norm is in eval mode."""
+
+    def __init__(self, cin, cout, k, stride=1, padding=0):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+
+    def forward(self, x, relu):
+        conv, bn = self.conv, self.bn
+        if bn.training:
+            y = bn(F.conv2d(x, conv.weight.to(x.dtype), None, conv.stride, conv.padding))
+        else:
+            w, b = _fold(conv.weight, bn, x.dtype)
+            y = F.conv2d(x, w, b, conv.stride, conv.padding)
+        return F.relu(y, inplace=True) if relu else y
+
+
+class _Bottleneck2D(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=False):
+        super().__init__()
+        self.cb1 = _ConvBN(inplanes, planes, 1)
+        self.cb2 = _ConvBN(planes, planes, 3, stride=stride, padding=1)     # style='pytorch': stride on the 3x3
+        self.cb3 = _ConvBN(planes, planes * 4, 1)
+        self.ds = _ConvBN(inplanes, planes * 4, 1, stride=stride) if downsample else None
+
+    def forward(self, x):
+        idt = self.ds(x, False) if self.ds is not None else x
+        out = self.cb3(self.cb2(self.cb1(x, True), True), False)
+        return F.relu(out + idt, inplace=True)
+
+
+class _BasicBlock2D(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=False):
+        super().__init__()
+        self.cb1 = _ConvBN(inplanes, planes, 3, stride=stride, padding=1)
+        self.cb2 = _ConvBN(planes, planes, 3, padding=1)
+        self.ds = _ConvBN(inplanes, planes, 1, stride=stride) if downsample else None
+
+    def forward(self, x):
+        idt = self.ds(x, False) if self.ds is not None else x
+        out = self.cb2(self.cb1(x, True), False)
+        return F.relu(out + idt, inplace=True)
+
+
+# state_dict names follow mmdet/torchvision: conv1/bn1, layer{i}.{j}.conv{k}/bn{k}, downsample.0/.1
+_RENAME = {'cb1.conv': 'conv1', 'cb1.bn': 'bn1', 'cb2.conv': 'conv2', 'cb2.bn': 'bn2', 'cb3.conv': 'conv3',
+           'cb3.bn': 'bn3', 'ds.conv': 'downsample.0', 'ds.bn': 'downsample.1', 'stem.conv': 'conv1', 'stem.bn': 'bn1'}
+
+
+@MODELS.register_module(name=['mmdet.ResNet', 'ResNet'])
+class ResNet(nn.Module):
+    arch_settings = {18: (_BasicBlock2D, (2, 2, 2, 2)), 34: (_BasicBlock2D, (3, 4, 6, 3)),
+                     50: (_Bottleneck2D, (3, 4, 6, 3)), 101: (_Bottleneck2D, (3, 4, 23, 3))}
+
+    def __init__(self, depth, in_channels=3, stem_channels=None, base_channels=64, num_stages=4,
+                 strides=(1, 2, 2, 2), dilations=(1, 1, 1, 1), out_indices=(0, 1, 2, 3), style='pytorch',
+                 frozen_stages=-1, norm_cfg=None, norm_eval=True, init_cfg=None, **kwargs):
+        super().__init__()
+        assert style == 'pytorch' and tuple(dilations) == (1, 1, 1, 1)
+        block, stage_blocks = self.arch_settings[depth]
+        stem_channels = stem_channels or base_channels
+        self.out_indices, self.frozen_stages, self.norm_eval = tuple(out_indices), frozen_stages, norm_eval
+        self.norm_requires_grad = (norm_cfg or {}).get('requires_grad', True)
+        self.stem = _ConvBN(in_channels, stem_channels, 7, stride=2, padding=3)
+        inplanes = stem_channels
+        self.num_stages = num_stages
+        for i in range(num_stages):
+            planes = base_channels * 2 ** i
+            blocks = []
+            for j in range(stage_blocks[i]):
+                stride = strides[i] if j == 0 else 1
+                ds = j == 0 and (stride != 1 or inplanes != planes * block.expansion)
+                blocks.append(block(inplanes, planes, stride=stride, downsample=ds))
+                inplanes = planes * block.expansion
+            setattr(self, f'layer{i + 1}', nn.Sequential(*blocks))
+        self.out_channels = [base_channels * 2 ** i * block.expansion for i in range(num_stages)]
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+        self._freeze()
+
+    def _freeze(self):
+        if not self.norm_requires_grad:
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    for p in m.parameters():
+                        p.requires_grad = False
+        if self.frozen_stages >= 0:
+            for p in self.stem.parameters():
+                p.requires_grad = False
+            for i in range(1, self.frozen_stages + 1):
+                for p in getattr(self, f'layer{i}').parameters():
+                    p.requires_grad = False
+
+    def train(self, mode=True):
+        super().train(mode)
+        if mode:
+            if self.frozen_stages >= 0:
+                self.stem.eval()
+                for i in range(1, self.frozen_stages + 1):
+                    getattr(self, f'layer{i}').eval()
+            if self.norm_eval:
+                for m in self.modules():
+                    if isinstance(m, nn.BatchNorm2d):
+                        m.eval()
+        return self
+
+    def forward(self, x):
+        x = self.stem(x, True)
+        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+        outs = []
+        for i in range(self.num_stages):
+            x = getattr(self, f'layer{i + 1}')(x)
+            if i in self.out_indices:
+                outs.append(x)
+        return tuple(outs)
+
+    # checkpoint compatibility with mmdet / torchvision parameter names
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        out = type(sd)()
+        for k, v in sd.items():
+            for a, b in _RENAME.items():
+                k = k.replace(a, b)
+            out[k] = v
+        return out
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        inv = {b: a for a, b in _RENAME.items()}
+        own = {k for k in super().state_dict(prefix=prefix).keys()}
+        for k in list(state_dict.keys()):
+            if not k.startswith(prefix) or k in own:
+                continue
+            tail = k[len(prefix):]
+            parts = tail.split('.')
+            new = None
+            if parts[0] in ('conv1', 'bn1') and len(parts) == 2:
+                new = 'stem.' + ('conv' if parts[0] == 'conv1' else 'bn') + '.' + parts[1]
+            elif parts[0].startswith('layer') and len(parts) >= 4:
+                mid = '.'.join(parts[2:-1])
+                if mid in inv:
+                    new = '.'.join(parts[:2] + [inv[mid], parts[-1]])
+            if new is not None:
+                state_dict[prefix + new] = state_dict.pop(k)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)

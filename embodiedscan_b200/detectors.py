@@ -1,0 +1,197 @@
+"""``SparseFeatureFusionSingleStage3DDetector`` and ``Det3DDataPreprocessor`` under the reference's registry names
+(embodiedscan/models/detectors/sparse_featfusion_single_stage.py:28-426,
+embodiedscan/models/data_preprocessors/data_preprocessor.py:23-339) — same constructor arguments and
+``forward(inputs, data_samples, mode)`` contract, so mmengine's ``train_step / val_step / test_step`` (mirrored
+here for the mmengine-less image) drive it unchanged.
+"""
+from typing import Dict, List, Optional, Union
+
+import math
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _ffi
+from . import sparse as SP
+from ._ffi import call, ptr, stream
+from .fusion import pack_paint_metas, pack_projections, paint_points
+from .registry import MODELS
+from .structures import InstanceData
+
+
+@MODELS.register_module()
+class Det3DDataPreprocessor(nn.Module):
+    """Image path of the reference preprocessor as one kernel: BGR->RGB, (x-mean)/std, right/bottom pad to a multiple
+    of ``pad_size_divisor``, multi-view stack; points pass through (``voxel=False`` is the only configured mode)."""
+
+    def __init__(self, mean=None, std=None, bgr_to_rgb=False, rgb_to_bgr=False, pad_size_divisor=1, pad_value=0,
+                 voxel=False, non_blocking=False, compute_dtype=torch.float32, **kwargs):
+        super().__init__()
+        assert not voxel, 'mmcv voxelisation wrappers are not on any configured path (SURVEY N14)'
+        assert not (bgr_to_rgb and rgb_to_bgr)
+        self.channel_conversion = bgr_to_rgb or rgb_to_bgr
+        self.mean = [float(m) for m in (mean or [0., 0., 0.])]
+        self.std = [float(s) for s in (std or [1., 1., 1.])]
+        self.pad_size_divisor, self.pad_value = pad_size_divisor, pad_value
+        self.compute_dtype = compute_dtype
+        self.register_buffer('_dev', torch.zeros(1), persistent=False)
+
+    @property
+    def device(self):
+        return self._dev.device
+
+    def forward(self, data: dict, training: bool = False) -> dict:
+        inputs, data_samples = data['inputs'], data.get('data_samples')
+        dev = self.device
+        out = {}
+        if 'points' in inputs:
+            out['points'] = [p.to(dev, non_blocking=True) for p in inputs['points']]
+        if 'img' in inputs:
+            imgs = inputs['img']
+            if isinstance(imgs, (list, tuple)):
+                shapes = {tuple(i.shape) for i in imgs}
+                assert len(shapes) == 1, 'views of a batch share one shape on the hot path'
+                imgs = torch.stack([i.to(dev, non_blocking=True) for i in imgs])
+            else:
+                imgs = imgs.to(dev, non_blocking=True)
+            if imgs.dim() == 4:
+                imgs = imgs[:, None]
+            assert imgs.dtype == torch.uint8, 'images arrive as uint8 CHW (Pack3DDetInputs)'
+            B, V, C, H, W = imgs.shape
+            d = self.pad_size_divisor
+            Hp, Wp = int(math.ceil(H / d) * d), int(math.ceil(W / d) * d)
+            buf = torch.empty((B * V, Hp, Wp, 3), dtype=self.compute_dtype, device=dev)
+            import ctypes
+            mean = (ctypes.c_float * 3)(*self.mean)
+            std = (ctypes.c_float * 3)(*self.std)
+            call('esb_img_normalize', ptr(imgs.contiguous()), B * V, H, W, Hp, Wp, ctypes.cast(mean, ctypes.c_void_p),
+                 ctypes.cast(std, ctypes.c_void_p), 1 if self.channel_conversion else 0, 1, ptr(buf),
+                 _ffi.dtype_code(self.compute_dtype), stream())
+            out['imgs'] = buf.view(B, V, Hp, Wp, 3).permute(0, 1, 4, 2, 3)   # (B,V,3,Hp,Wp), channels-last memory
+            if data_samples is not None:
+                for ds in data_samples:
+                    ds.set_metainfo({'batch_input_shape': (Hp, Wp), 'pad_shape': (Hp, Wp)})
+        elif 'imgs' in inputs:
+            out['imgs'] = inputs['imgs'].to(dev)
+        if data_samples is not None:
+            for ds in data_samples:
+                if 'gt_instances_3d' in ds:
+                    ds.gt_instances_3d.to(dev)
+        return {'inputs': out, 'data_samples': data_samples}
+
+
+@MODELS.register_module()
+class SparseFeatureFusionSingleStage3DDetector(nn.Module):
+
+    def __init__(self, backbone, backbone_3d, bbox_head, neck=None, neck_3d=None, coord_type: str = 'CAMERA',
+                 train_cfg: Optional[dict] = None, test_cfg: Optional[dict] = None,
+                 data_preprocessor: Optional[dict] = None, use_xyz_feat: bool = False, init_cfg: Optional[dict] = None,
+                 compute_dtype=torch.float32):
+        super().__init__()
+        assert neck is None and neck_3d is None, 'no configured hot-path model uses neck / neck_3d here'
+        self.compute_dtype = compute_dtype
+        if isinstance(data_preprocessor, dict):
+            data_preprocessor = dict(data_preprocessor, compute_dtype=compute_dtype)
+            data_preprocessor.setdefault('type', 'Det3DDataPreprocessor')
+        self.data_preprocessor = MODELS.build(data_preprocessor) if data_preprocessor is not None else None
+        self.backbone = MODELS.build(backbone)
+        self.backbone_3d = MODELS.build(backbone_3d)
+        bbox_head = dict(bbox_head)
+        bbox_head.update(train_cfg=train_cfg)
+        bbox_head.update(test_cfg=test_cfg)
+        self.bbox_head = MODELS.build(bbox_head)
+        self.coord_type = coord_type
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.voxel_size = bbox_head['voxel_size']
+        self.use_xyz_feat = use_xyz_feat
+
+    # ---- feature extraction (sparse_featfusion_single_stage.py:86-221) --------------------------------------
+    def voxelize(self, points: List[torch.Tensor]):
+        dev = points[0].device
+        n_tot = sum(p.shape[0] for p in points)
+        coords = torch.empty((n_tot, 4), dtype=torch.int32, device=dev)
+        inv = float(np.float32(1.) / np.float32(self.voxel_size))
+        off = 0
+        feats = []
+        for b, p in enumerate(points):
+            p = p.float().contiguous()
+            call('esb_voxelize_points', ptr(p), p.shape[0], p.shape[1], b, inv, ptr(coords[off:]), stream())
+            off += p.shape[0]
+            feats.append(p if self.use_xyz_feat else p[:, 3:])
+        return coords, torch.cat(feats)
+
+    def extract_feat(self, batch_inputs_dict: Dict[str, torch.Tensor], batch_data_samples) -> List[SP.SparseTensor]:
+        points = batch_inputs_dict['points']
+        coordinates, features = self.voxelize(points)
+        x = SP.SparseTensor(coordinates=coordinates, features=features.to(self.compute_dtype))
+        x = self.backbone_3d(x)
+        num_levels = len(x)
+
+        img = batch_inputs_dict['imgs']
+        batch_img_metas = [ds.metainfo for ds in batch_data_samples]
+        assert img.dim() == 5, 'multi-view input (B, n_views, C, H, W)'
+        B, V = img.shape[:2]
+        img4 = img.reshape([-1] + list(img.shape)[2:]).to(self.compute_dtype)
+        if not img4.is_contiguous(memory_format=torch.channels_last):
+            img4 = img4.contiguous(memory_format=torch.channels_last)
+        img_features = self.backbone(img4)
+
+        dev = img.device
+        metas = pack_paint_metas(batch_img_metas, dev)
+        proj = pack_projections(batch_img_metas, self.coord_type, dev)
+        pad_hw = tuple(img.shape[-2:])
+        for level_idx in range(num_levels):
+            painted = paint_points(img_features[level_idx], x[level_idx].C, metas, proj, self.voxel_size, pad_hw, V)
+            x[level_idx] = x[level_idx].replace_feature(torch.cat([x[level_idx].F, painted.to(x[level_idx].F.dtype)], 1))
+        return x
+
+    def loss(self, batch_inputs_dict, batch_data_samples, **kwargs):
+        x = self.extract_feat(batch_inputs_dict, batch_data_samples)
+        return self.bbox_head.loss(x, batch_data_samples, **kwargs)
+
+    def predict(self, batch_inputs_dict, batch_data_samples, **kwargs):
+        x = self.extract_feat(batch_inputs_dict, batch_data_samples)
+        results_list = self.bbox_head.predict(x, batch_data_samples, **kwargs)
+        return self.add_pred_to_datasample(batch_data_samples, results_list)
+
+    def forward(self, inputs: Union[dict, List[dict]], data_samples=None, mode: str = 'tensor', **kwargs):
+        if mode == 'loss':
+            return self.loss(inputs, data_samples, **kwargs)
+        if mode == 'predict':
+            return self.predict(inputs, data_samples, **kwargs)
+        raise RuntimeError(f'Invalid mode "{mode}". Only supports loss and predict mode')
+
+    @staticmethod
+    def add_pred_to_datasample(data_samples, data_instances_3d=None, data_instances_2d=None):
+        assert data_instances_3d is not None or data_instances_2d is not None
+        if data_instances_2d is None:
+            data_instances_2d = [InstanceData() for _ in range(len(data_instances_3d))]
+        if data_instances_3d is None:
+            data_instances_3d = [InstanceData() for _ in range(len(data_instances_2d))]
+        for i, ds in enumerate(data_samples):
+            ds.pred_instances_3d = data_instances_3d[i]
+            ds.pred_instances = data_instances_2d[i]
+        return data_samples
+
+    # ---- mmengine BaseModel contract (†upstream) -------------------------------------------------------------
+    def train_step(self, data, optim_wrapper):
+        data = self.data_preprocessor(data, True)
+        losses = self(**data, mode='loss')
+        loss, log_vars = parse_losses(losses)
+        optim_wrapper.update_params(loss)
+        return log_vars
+
+    @torch.no_grad()
+    def val_step(self, data):
+        data = self.data_preprocessor(data, False)
+        return self(**data, mode='predict')
+
+    test_step = val_step
+
+
+def parse_losses(losses: dict):
+    """mmengine BaseModel.parse_losses: total = sum of every entry whose key contains 'loss'."""
+    log_vars = {k: (v.mean() if isinstance(v, torch.Tensor) else sum(x.mean() for x in v)) for k, v in losses.items()}
+    loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+    log_vars['loss'] = loss
+    return loss, log_vars

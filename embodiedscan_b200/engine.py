@@ -1,0 +1,148 @@
+"""Training-step runtime for the hot path: flat parameter/gradient arenas, fused clip + AdamW kernels, and data-parallel
+gradient all-reduce over NCCL (NVLink 5 / NVSwitch) launched per bucket as soon as a bucket's gradients are complete.
+
+Replaces, for this path, mmengine's OptimWrapper + MMDistributedDataParallel (†upstream; optimizer and clip settings at
+configs/detection/mv-det3d_8xb4_embodiedscan-3d-284class-9dof.py:219-223): one process per GPU, scans sharded across
+ranks, the only bulk collective is the gradient SUM (averaged inside the AdamW kernel), no host synchronisation.
+"""
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from ._ffi import call, ptr, stream
+
+
+class FlatArena:
+    """All trainable parameters live in ONE contiguous fp32 buffer, their gradients in another (same offsets)."""
+
+    def __init__(self, model: nn.Module, bucket_bytes: int = 64 << 20):
+        params = [p for p in model.parameters() if p.requires_grad]
+        # reverse registration order ~ the order autograd finishes gradients, so buckets complete front to back
+        params = params[::-1]
+        self.params = params
+        dev = params[0].device
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned
+        self.numel = n
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.offsets = offs
+        for p, o in zip(params, offs):
+            self.flat[o:o + p.numel()].copy_(p.data.reshape(-1).float())
+            p.data = self.flat[o:o + p.numel()].view_as(p)
+            p.grad = self.grad[o:o + p.numel()].view_as(p)
+        # buckets: contiguous [start, end) ranges of ~bucket_bytes
+        self.buckets, self.bucket_of = [], []
+        start, cur = 0, 0
+        per = max(bucket_bytes // 4, 1)
+        for i, (p, o) in enumerate(zip(params, offs)):
+            end = o + (p.numel() + 3) // 4 * 4
+            self.bucket_of.append(len(self.buckets))
+            if end - start >= per or i == len(params) - 1:
+                self.buckets.append((start, end))
+                start = end
+        self.n_params_in_bucket = [0] * len(self.buckets)
+        for b in self.bucket_of:
+            self.n_params_in_bucket[b] += 1
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):  # autograd may have replaced .grad; re-point it at the arena
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+
+class DataParallelReducer:
+    """Per-bucket asynchronous all-reduce(SUM) of the gradient arena, overlapped with the rest of backward."""
+
+    def __init__(self, arena: FlatArena, process_group=None):
+        self.arena, self.group = arena, process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.pending = [0] * len(arena.buckets)
+        self.handles = []
+        self.launched = [False] * len(arena.buckets)
+        if self.world > 1:
+            for i, p in enumerate(arena.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(arena.bucket_of[i]))
+        self.reset()
+
+    def reset(self):
+        self.pending = list(self.arena.n_params_in_bucket)
+        self.launched = [False] * len(self.arena.buckets)
+        self.handles = []
+
+    def _launch(self, b):
+        s, e = self.arena.buckets[b]
+        self.handles.append(dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.launched[b] = True
+
+    def _make_hook(self, b):
+        def hook(_p):
+            self.pending[b] -= 1
+            if self.pending[b] == 0 and not self.launched[b]:
+                self._launch(b)
+        return hook
+
+    def finish(self):
+        """Reduce whatever was not launched by hooks (parameters unused this step), then wait."""
+        if self.world > 1:
+            for b in range(len(self.arena.buckets)):
+                if not self.launched[b]:
+                    self._launch(b)
+            for h in self.handles:
+                h.wait()
+        self.reset()
+
+
+class FusedAdamW:
+    """AdamW + global-norm clipping over the arena: two kernel launches per step, no host sync."""
+
+    def __init__(self, arena: FlatArena, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_norm=10.0,
+                 world_size: int = 1):
+        self.arena, self.lr, self.betas, self.eps, self.wd, self.max_norm = arena, lr, betas, eps, weight_decay, max_norm
+        self.world = world_size
+        dev = arena.flat.device
+        self.m = torch.zeros_like(arena.flat)
+        self.v = torch.zeros_like(arena.flat)
+        self.state = torch.zeros(3, dtype=torch.float32, device=dev)   # sumsq, norm, clip coefficient
+        self.step_count = 0
+
+    def step(self):
+        a = self.arena
+        self.step_count += 1
+        ws = 1.0 / self.world                         # arena.grad holds the SUM over ranks
+        call('esb_grad_clip_coef', ptr(a.grad), a.numel, float(self.max_norm if self.max_norm else 0.), ws,
+             ptr(self.state), stream())
+        call('esb_adamw_step', ptr(a.flat), ptr(a.grad), ptr(self.m), ptr(self.v), None, a.numel, self.lr, self.betas[0],
+             self.betas[1], self.eps, self.wd, self.step_count, ws, ptr(self.state), stream())
+
+    @property
+    def grad_norm(self):
+        return self.state[1]
+
+
+class OptimWrapper:
+    """``update_params(loss)`` of mmengine's OptimWrapper for the arena optimiser."""
+
+    def __init__(self, model: nn.Module, lr=1e-3, weight_decay=1e-4, max_norm=10.0, process_group=None,
+                 bucket_bytes: int = 64 << 20):
+        self.arena = FlatArena(model, bucket_bytes)
+        world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.reducer = DataParallelReducer(self.arena, process_group)
+        self.optimizer = FusedAdamW(self.arena, lr=lr, weight_decay=weight_decay, max_norm=max_norm, world_size=world)
+        self.arena.zero_grad()
+
+    def update_params(self, loss: torch.Tensor):
+        loss.backward()
+        self.reducer.finish()
+        self.optimizer.step()
+        self.arena.zero_grad()
+
+
+def broadcast_parameters(arena: FlatArena, src: int = 0, process_group=None):
+    if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        dist.broadcast(arena.flat, src=src, group=process_group)

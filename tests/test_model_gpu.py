@@ -1,0 +1,98 @@
+"""End-to-end parity of the registered detector (built from the reference-shaped config dict) against the CPU oracle
+on BASELINE.json config C1 (1-2 scans x 2 views 240x320, 2k points, ResNet-18/16 + MinkResNet14), fp32."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _setup(n_scans=1, augment=False, variant='C1', seed=0, cls_bias=None):
+    from embodiedscan_b200 import MODELS
+    from embodiedscan_b200.synth import mv_det3d_config, synth_batch
+    from oracle import model_ref as M
+    torch.manual_seed(seed)
+    cfg = mv_det3d_config(variant)
+    model = MODELS.build(cfg).to(DEV)
+    if cls_bias is not None:
+        with torch.no_grad():
+            model.bbox_head.conv_cls.bias.fill_(cls_bias)
+    batch = synth_batch(0, n_scans, n_views=2, H=240, W=320, n_points=2000, augment=augment)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    return cfg, model, batch, sd, imgs
+
+
+@pytest.mark.parametrize('n_scans,augment', [(1, False), (2, True)])
+def test_loss_and_gradients_match_oracle(n_scans, augment):
+    from oracle import model_ref as M
+    cfg, model, batch, sd, imgs = _setup(n_scans, augment)
+    model.train()
+    watch = ['bbox_head.conv_cls.kernel', 'bbox_head.conv_reg.kernel', 'bbox_head.out_block_0.0.kernel',
+             'bbox_head.up_block_1.0.kernel', 'backbone_3d.conv1.kernel', 'backbone_3d.layer2.0.conv1.kernel',
+             'backbone_3d.layer1.0.norm1.bn.weight', 'backbone.layer2.0.cb1.conv.weight', 'bbox_head.scales.1.scale']
+    for k in watch:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    ref = M.detector_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
+    sum(ref.values()).backward()
+    data = model.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
+    losses = model(**data, mode='loss')
+    sum(losses.values()).backward()
+    for k in ('loss_center', 'loss_bbox', 'loss_cls'):
+        a, b = float(losses[k]), float(ref[k])
+        assert abs(a - b) <= 1e-3 * max(abs(b), 1e-3), (k, a, b)
+    assert float(ref['loss_bbox']) > 0, 'the scene must contain positives'
+    params = dict(model.named_parameters())
+    name_map = {'backbone.layer2.0.cb1.conv.weight': 'backbone.layer2.0.cb1.conv.weight'}
+    for k in watch:
+        g, gr = params[name_map.get(k, k)].grad.cpu(), sd[k].grad
+        scale = float(gr.abs().max())
+        assert float((g - gr).abs().max()) <= 2e-3 * max(scale, 1e-6), (k, float((g - gr).abs().max()), scale)
+
+
+def test_predict_matches_oracle():
+    from oracle import model_ref as M
+    cfg, model, batch, sd, imgs = _setup(1, False, cls_bias=-1.5)
+    model.eval()
+    with torch.no_grad():
+        ref = M.detector_predict(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
+        out = model.val_step(dict(inputs=batch['inputs'], data_samples=batch['data_samples']))
+    rb, rs, rl = ref[0]
+    pred = out[0].pred_instances_3d
+    assert rl.numel() > 10, 'the test must exercise NMS'
+    assert torch.equal(pred.labels_3d.cpu(), rl), 'NMS selection order must be identical'
+    assert float((pred.scores_3d.cpu() - rs).abs().max()) < 1e-5
+    box = pred.bboxes_3d.tensor.cpu()
+    assert box.shape[1] == 9 and float(box[:, 7:].abs().max()) == 0.0      # 9-DoF -> 7 -> padded back
+    assert float((box[:, :7] - rb).abs().max()) <= 1e-3 * float(rb.abs().max())
+
+
+def test_bf16_step_tracks_fp32():
+    from embodiedscan_b200 import MODELS
+    from embodiedscan_b200.synth import mv_det3d_config, synth_batch
+    torch.manual_seed(0)
+    cfg = mv_det3d_config('C1')
+    m32 = MODELS.build(cfg).to(DEV).train()
+    m16 = MODELS.build(dict(cfg, compute_dtype=torch.bfloat16)).to(DEV).train()
+    m16.load_state_dict(m32.state_dict())
+    batch = synth_batch(0, 1, n_views=2, H=240, W=320, n_points=2000)
+    out = []
+    for m in (m32, m16):
+        data = m.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
+        out.append({k: float(v) for k, v in m(**data, mode='loss').items()})
+    for k in out[0]:
+        assert abs(out[0][k] - out[1][k]) <= 0.05 * max(abs(out[0][k]), 1e-2), (k, out)
+
+
+def test_train_steps_reduce_loss():
+    from embodiedscan_b200.engine import OptimWrapper
+    cfg, model, batch, sd, imgs = _setup(1, True)
+    model.train()
+    ow = OptimWrapper(model, lr=1e-3)
+    hist = []
+    for _ in range(6):
+        logs = model.train_step(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), ow)
+        hist.append(float(logs['loss']))
+    assert all(np.isfinite(hist)) and hist[-1] < hist[0], hist

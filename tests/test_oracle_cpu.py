@@ -1,0 +1,140 @@
+"""CPU: pin the oracle with closed forms and the reference's only known-answer vector (parity is otherwise unpinned:
+the reference ships no tests or fixtures — oracle/__init__.py)."""
+import math
+
+import numpy as np
+import torch
+
+from oracle import geometry_ref as G
+from oracle import model_ref as M
+from oracle import sparse_ref as S
+
+
+def test_weighted_loss_docstring_vector():
+    """embodiedscan/models/losses/reduce_loss.py:80-96: l1 of pred [0,2,3] vs target [1,1,1], weight [1,0,1]."""
+    loss = (torch.tensor([0., 2., 3.]) - torch.tensor([1., 1., 1.])).abs()
+    w = torch.tensor([1., 0., 1.])
+    assert abs(float(loss.mean()) - 1.3333) < 1e-4
+    assert float((loss * w).mean()) == 1.0
+    assert torch.equal(loss, torch.tensor([1., 1., 2.]))
+    assert float((loss * w).sum() / 2) == 1.5
+
+
+def test_unique_first_order_and_strides():
+    c = np.array([[0, 5, 5, 5], [0, 1, 1, 1], [0, 5, 5, 5], [0, -1, -1, -1], [1, 1, 1, 1], [0, 1, 1, 1]])
+    out, inv = S.unique_first(c)
+    assert out.tolist() == [[0, 5, 5, 5], [0, 1, 1, 1], [0, -1, -1, -1], [1, 1, 1, 1]] and inv.tolist() == [0, 1, 0, 2, 3, 1]
+    out2, _ = S.unique_first(c, 2)
+    assert out2.tolist() == [[0, 4, 4, 4], [0, 0, 0, 0], [0, -2, -2, -2], [1, 0, 0, 0]]   # floor, not truncation
+
+
+def test_conv_counts_neighbours_and_isolated_voxel():
+    c = np.array([[0, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 9, 9, 9]])
+    nbr = S.kernel_map(c, c, S.offsets(3, 1))
+    y = S.conv(torch.ones(4, 1), torch.ones(27, 1, 1), nbr)
+    assert y.view(-1).tolist() == [3., 3., 3., 1.]   # (1,0,0) and (0,1,0) are diagonal neighbours
+    w = torch.randn(27, 3, 5)
+    x = torch.randn(4, 3)
+    assert torch.allclose(S.conv(x, w, nbr)[3], x[3] @ w[13])          # isolated voxel: centre tap only (k = 13)
+
+
+def test_conv_dense_equivalence():
+    D, cin, cout = 5, 4, 6
+    zz, yy, xx = np.meshgrid(np.arange(D), np.arange(D), np.arange(D), indexing='ij')
+    c = np.stack([np.zeros(D ** 3, dtype=np.int64), xx.ravel(), yy.ravel(), zz.ravel()], 1)
+    x, w = torch.randn(D ** 3, cin), torch.randn(27, cin, cout)
+    dense = x.view(D, D, D, cin).permute(3, 0, 1, 2)[None]
+    wd = w.view(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2)
+    ref = torch.nn.functional.conv3d(dense, wd, padding=1)[0].permute(1, 2, 3, 0).reshape(-1, cout)
+    assert torch.allclose(S.conv(x, w, S.kernel_map(c, c, S.offsets(3, 1))), ref, atol=1e-4)
+
+
+def test_generative_and_union():
+    p = np.array([[0, 0, 0, 0], [0, 4, 0, 0]])
+    ch = S.generative_children(p, 2)
+    assert ch.shape == (16, 4) and ch[1].tolist() == [0, 2, 0, 0] and ch[8 + 6].tolist() == [0, 4, 2, 2]
+    a = np.array([[0, 2, 0, 0], [0, 8, 8, 8]])
+    u, mb = S.union(a, ch)
+    assert u.shape[0] == 2 + 15 and mb[1] == 0 and mb[0] == 2
+
+
+def test_euler_zxy_formulas_and_round_trip():
+    e = torch.tensor([[0.3, -0.2, 0.5], [2.5, 0.4, -1.0]])
+    R = G.euler_to_matrix(e)
+    a, b, c = e[0]
+    Rz = torch.tensor([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1.]])
+    Rx = torch.tensor([[1., 0, 0], [0, math.cos(b), -math.sin(b)], [0, math.sin(b), math.cos(b)]])
+    Ry = torch.tensor([[math.cos(c), 0, math.sin(c)], [0, 1., 0], [-math.sin(c), 0, math.cos(c)]])
+    assert torch.allclose(R[0], Rz @ Rx @ Ry, atol=1e-6)
+    assert torch.allclose(G.matrix_to_euler_zxy(R), e, atol=1e-5)
+    m = G.ortho_6d_2_mat(torch.randn(5, 3), torch.randn(5, 3))
+    assert torch.allclose(m @ m.transpose(1, 2), torch.eye(3).expand(5, 3, 3), atol=1e-5)
+
+
+def test_chamfer_closed_forms():
+    box = torch.tensor([[0.2, -0.1, 0.5, 1.0, 2.0, 0.8, 0.3, 0.05, -0.02]])
+    assert float(G.chamfer_l1_mean(box, box)) == 0.0
+    t = torch.tensor([0.05, -0.03, 0.02])
+    moved = box.clone()
+    moved[:, :3] += t
+    assert abs(float(G.chamfer_l1_mean(moved, box)) - float(t.abs().sum())) < 1e-6
+
+
+def test_bev_iou_closed_forms():
+    a = np.array([0, 0, 0, 2, 2, 1, 0], dtype=np.float32)
+    assert abs(G.iou_bev(a, a) - 1) < 1e-6
+    assert abs(G.iou_bev(a, np.array([1, 0, 0, 2, 2, 1, 0], dtype=np.float32)) - 1 / 3) < 1e-6
+    oct_area = 8 * (math.sqrt(2) - 1)
+    assert abs(G.iou_bev(a, np.array([0, 0, 5, 2, 2, 9, math.pi / 4], dtype=np.float32)) - oct_area / (8 - oct_area)) < 1e-5
+    assert G.iou_bev(a, np.array([5, 5, 0, 1, 1, 1, 0.3], dtype=np.float32)) == 0
+    keep = G.nms3d(np.stack([a, a, np.array([5, 5, 0, 1, 1, 1, 0], np.float32)]), np.array([.5, .9, .1]), 0.5)
+    assert keep.tolist() == [1, 2]
+
+
+def test_focal_closed_form():
+    v = G.sigmoid_focal_loss_sum(torch.zeros(1, 4), torch.tensor([2]))
+    assert abs(float(v) - (0.25 * 0.25 + 3 * 0.75 * 0.25) * math.log(2)) < 1e-6
+    v = G.sigmoid_focal_loss_sum(torch.zeros(2, 4), torch.tensor([-1, -1]))
+    assert abs(float(v) - 8 * 0.75 * 0.25 * math.log(2)) < 1e-6
+
+
+def test_projection_identity_extrinsic():
+    K = np.eye(4, dtype=np.float32)
+    K[0, 0] = K[1, 1] = 100.
+    K[0, 2], K[1, 2] = 32., 24.
+    P = torch.from_numpy(M.compose_projection(K, np.eye(4, dtype=np.float32)))[None]
+    feat = torch.arange(48 * 64, dtype=torch.float32).view(1, 1, 48, 64)
+    pts = torch.tensor([[0., 0., 2.], [0.1, -0.05, 1.], [0., 0., -1.], [5., 0., 1.]])
+    out, cnt = M.batch_point_sample(dict(img_shape=(48, 64)), feat, pts, P, (48, 64))
+    # u = 100*x/z + 32, v = 100*y/z + 24 ; nearest with align_corners: ix = round(u/64*63)
+    assert cnt.tolist() == [1, 1, 0, 0]
+    assert float(out[0]) == round(24 / 48 * 47) * 64 + round(32 / 64 * 63)
+    assert float(out[1]) == round(19 / 48 * 47) * 64 + round(42 / 64 * 63)
+    assert float(out[2]) == 0 and float(out[3]) == 0
+
+
+def test_get_targets_hand_countable():
+    box = torch.tensor([[0., 0., 0., 2., 2., 2., 0., 0., 0.]])
+    g = torch.arange(-9, 10).float() * 0.1
+    fine = torch.stack(torch.meshgrid(g, g, torch.tensor([0.0]), indexing='ij'), -1).view(-1, 3)   # 361 inside
+    coarse = torch.tensor([[0.05, 0.0, 0.0], [3.0, 3.0, 3.0]])
+    ct, bt, kt = M.get_targets([fine, coarse], box, torch.tensor([7]), assign_thr=27, center_thr=18)
+    # level 0 has 361 >= 27 points inside, level 1 has 1 < 27 -> best level = 0. Centerness tiers on the symmetric grid:
+    # 1 (centre) + 4 + 4 + 4 = 13, the next tier holds 8 tied points so the 19th largest value lies inside it and the
+    # strict `>` drops the whole tier: "keeps <= 18"  -> 13 positives.
+    assert int((kt == 7).sum()) == 13 and int((kt[-2:] == 7).sum()) == 0
+    assert float(ct[kt == 7].min()) > 0.7
+
+
+def test_oracle_detector_runs_c1():
+    from embodiedscan_b200 import MODELS
+    from embodiedscan_b200.synth import mv_det3d_config, synth_batch
+    torch.manual_seed(0)
+    cfg = mv_det3d_config('C1')
+    sd = {k: v.detach().clone() for k, v in MODELS.build(cfg).state_dict().items()}
+    batch = synth_batch(0, 1, n_views=2, H=240, W=320, n_points=2000)
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    with torch.no_grad():
+        losses = M.detector_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
+    assert all(torch.isfinite(v) for v in losses.values()) and float(losses['loss_cls']) > 0
