@@ -98,6 +98,13 @@ class _ConvBN(nn.Module):
         self.bn = nn.BatchNorm2d(cout)
 
     def forward(self, x, relu):
+        if x.dtype == torch.float32 and x.is_cuda and torch.backends.cudnn.allow_tf32:
+            # fp32 is the parity arithmetic: keep cuDNN out of TF32 (10-bit mantissa breaks the 1e-3 bound)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return self._forward(x, relu)
+        return self._forward(x, relu)
+
+    def _forward(self, x, relu):
         conv, bn = self.conv, self.bn
         if bn.training:
             y = bn(F.conv2d(x, conv.weight.to(x.dtype), None, conv.stride, conv.padding))

@@ -18,7 +18,7 @@ def _setup(n_scans=1, augment=False, variant='C1', seed=0, cls_bias=None):
     if cls_bias is not None:
         with torch.no_grad():
             model.bbox_head.conv_cls.bias.fill_(cls_bias)
-    batch = synth_batch(0, n_scans, n_views=2, H=240, W=320, n_points=2000, augment=augment)
+    batch = synth_batch(1, n_scans, n_views=2, H=240, W=320, n_points=2000, augment=augment)
     sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
                              cfg['data_preprocessor']['std'])
@@ -45,16 +45,31 @@ def test_loss_and_gradients_match_oracle(n_scans, augment):
         assert abs(a - b) <= 1e-3 * max(abs(b), 1e-3), (k, a, b)
     assert float(ref['loss_bbox']) > 0, 'the scene must contain positives'
     params = dict(model.named_parameters())
-    name_map = {'backbone.layer2.0.cb1.conv.weight': 'backbone.layer2.0.cb1.conv.weight'}
+    report = {}
     for k in watch:
-        g, gr = params[name_map.get(k, k)].grad.cpu(), sd[k].grad
-        scale = float(gr.abs().max())
-        assert float((g - gr).abs().max()) <= 2e-3 * max(scale, 1e-6), (k, float((g - gr).abs().max()), scale)
+        g, gr = params[k].grad.cpu(), sd[k].grad
+        report[k] = (float((g - gr).abs().max()) / max(float(gr.abs().max()), 1e-9),
+                     float((g - gr).norm()) / max(float(gr.norm()), 1e-9))
+    print('gradient parity (max-rel, l2-rel):', report)
+    for k, (mx, l2) in report.items():
+        assert mx <= 2e-3 and l2 <= 2e-3, (k, mx, l2)
 
 
 def test_predict_matches_oracle():
     from oracle import model_ref as M
-    cfg, model, batch, sd, imgs = _setup(1, False, cls_bias=-1.5)
+    cfg, model, batch, sd, imgs = _setup(1, False)
+    # three classes clear the score threshold (the oracle NMS is a scalar python loop), top-50 per level exercises topk
+    with torch.no_grad():
+        bias = torch.full((284, ), -9.0)
+        bias[[3, 77, 200]] = -1.5
+        model.bbox_head.conv_cls.bias.copy_(bias.view(1, -1))
+        model.bbox_head.conv_cls.kernel.mul_(20.)
+        model.bbox_head.conv_center.kernel.mul_(20.)
+    sd['bbox_head.conv_cls.bias'] = model.bbox_head.conv_cls.bias.detach().cpu().clone()
+    sd['bbox_head.conv_cls.kernel'] = model.bbox_head.conv_cls.kernel.detach().cpu().clone()
+    sd['bbox_head.conv_center.kernel'] = model.bbox_head.conv_center.kernel.detach().cpu().clone()
+    cfg = dict(cfg, test_cfg=dict(nms_pre=50, iou_thr=.5, score_thr=.01))
+    model.bbox_head.test_cfg = cfg['test_cfg']
     model.eval()
     with torch.no_grad():
         ref = M.detector_predict(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
@@ -63,7 +78,7 @@ def test_predict_matches_oracle():
     pred = out[0].pred_instances_3d
     assert rl.numel() > 10, 'the test must exercise NMS'
     assert torch.equal(pred.labels_3d.cpu(), rl), 'NMS selection order must be identical'
-    assert float((pred.scores_3d.cpu() - rs).abs().max()) < 1e-5
+    assert float((pred.scores_3d.cpu() - rs).abs().max()) < 1e-4
     box = pred.bboxes_3d.tensor.cpu()
     assert box.shape[1] == 9 and float(box[:, 7:].abs().max()) == 0.0      # 9-DoF -> 7 -> padded back
     assert float((box[:, :7] - rb).abs().max()) <= 1e-3 * float(rb.abs().max())
@@ -77,7 +92,7 @@ def test_bf16_step_tracks_fp32():
     m32 = MODELS.build(cfg).to(DEV).train()
     m16 = MODELS.build(dict(cfg, compute_dtype=torch.bfloat16)).to(DEV).train()
     m16.load_state_dict(m32.state_dict())
-    batch = synth_batch(0, 1, n_views=2, H=240, W=320, n_points=2000)
+    batch = synth_batch(1, 1, n_views=2, H=240, W=320, n_points=2000)
     out = []
     for m in (m32, m16):
         data = m.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)

@@ -132,7 +132,7 @@ def test_oracle_detector_runs_c1():
     torch.manual_seed(0)
     cfg = mv_det3d_config('C1')
     sd = {k: v.detach().clone() for k, v in MODELS.build(cfg).state_dict().items()}
-    batch = synth_batch(0, 1, n_views=2, H=240, W=320, n_points=2000)
+    batch = synth_batch(1, 1, n_views=2, H=240, W=320, n_points=2000)
     imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
                              cfg['data_preprocessor']['std'])
     with torch.no_grad():
