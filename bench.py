@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — training scans/sec of the mv-3ddet hot path (BASELINE.json config C2: ResNet-50/16 + MinkResNet34,
+20 views 480x640, 100k points, bf16) on N B200s of one node, data-parallel over scans.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                      (the CPU port of the reference path on the host cores)
+
+One JSON line on rank 0. `value`: device-resident inputs, fwd + loss + bwd + grad all-reduce + clip + AdamW, timed with
+CUDA events, max over ranks. `e2e`: the same step through model.train_step with pinned HOST inputs (H2D inside the timed
+region, loss read back). `roofline`: the sparse-conv gather/GEMM/scatter kernel, algorithmic bytes (pair model,
+BASELINE.md §3) / CUDA-event time of its launches inside the timed region. `cpu_baseline`: oracle port on host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'training scans/sec mv-3ddet 20-view (ResNet-50/16 + MinkResNet34, 480x640, 100k pts)'
+UNIT = 'scans/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='esb200', choices=['esb200', 'reference'])
+    ap.add_argument('--batch', type=int, default=4, help='scans per GPU per step (cfg :181 batch_size=4)')
+    ap.add_argument('--views', type=int, default=20)
+    ap.add_argument('--height', type=int, default=480)
+    ap.add_argument('--width', type=int, default=640)
+    ap.add_argument('--points', type=int, default=100000)
+    ap.add_argument('--variant', default='C2')
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+def _trainable(k, v):
+    """Parameters the reference trains: everything but running stats, the frozen 2D stem/stage 1 and the 2D BNs."""
+    if not v.is_floating_point() or 'running_' in k or 'num_batches' in k:
+        return False
+    if k.startswith('backbone.'):
+        return k.endswith('.conv.weight') and not (k.startswith('backbone.stem') or k.startswith('backbone.layer1.'))
+    return True
+
+
+def oracle_step(sd, cfg, scan, backward=True):
+    """One CPU step of the oracle port on one scan: forward + loss (+ backward through autograd)."""
+    from oracle import model_ref as M
+    imgs = M.preprocess_imgs(scan['img'][None].cpu(), cfg['data_preprocessor']['mean'], cfg['data_preprocessor']['std'])
+    if backward:
+        for k, v in sd.items():
+            v.requires_grad_(_trainable(k, v))
+    losses = M.detector_loss(sd, cfg, [scan['points'].cpu()], imgs, [scan['data_sample']])
+    total = sum(losses.values())
+    if backward:
+        total.backward()
+        for v in sd.values():
+            v.grad = None
+    return float(total)
+
+
+def cpu_baseline(cfg, variant_args, budget_s=30.0, backward=True, max_steps=None):
+    """Oracle port timed on the host cores on a bounded sample (whole scans of the same shape)."""
+    from embodiedscan_b200 import MODELS
+    from embodiedscan_b200.synth import synth_scan
+    torch.manual_seed(0)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().clone().float() for k, v in MODELS.build(cfg).state_dict().items()}
+    scan = synth_scan(0, device='cpu', **variant_args)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        oracle_step(sd, cfg, scan, backward)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or (max_steps is not None and n >= max_steps) or el / n * (n + 1) > 2.5 * budget_s:
+            break
+    return {'value': n / el, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'{n} scan(s) of the workload shape, forward + loss' + (' + backward' if backward else '') +
+                      ' (no optimiser step), oracle restatement in torch-CPU fp32 — the reference stack '
+                      '(MinkowskiEngine / mmcv / pytorch3d / mmdet / mmengine) is not installable here',
+            'seconds': el}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    from embodiedscan_b200.synth import mv_det3d_config
+    cfg = mv_det3d_config(args.variant)
+    va = dict(n_views=args.views, H=args.height, W=args.width, n_points=args.points)
+    # each "step" = one scan through the CPU port; bounded so K + W steps end within a few minutes
+    base = cpu_baseline(cfg, va, budget_s=min(150.0, 12.0 * max(args.steps, 1)), backward=True, max_steps=args.steps)
+    out = {'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': 1000.0 / base['value'], 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+           'config': {'workload': f'{args.variant}: mv-3ddet 1 scan/step x {args.views} views {args.height}x{args.width}, '
+                                  f'{args.points} points, CPU port'},
+           'cpu_baseline': base,
+           'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from embodiedscan_b200 import MODELS, _ffi
+    from embodiedscan_b200 import sparse as SP
+    from embodiedscan_b200.engine import OptimWrapper, broadcast_parameters
+    from embodiedscan_b200.synth import mv_det3d_config, synth_scan
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    torch.manual_seed(0)
+    cfg = mv_det3d_config(args.variant)
+    model = MODELS.build(dict(cfg, compute_dtype=dtype)).to(dev).train()
+    optim = OptimWrapper(model, lr=1e-3, weight_decay=1e-4, max_norm=10.0)
+    broadcast_parameters(optim.arena)
+
+    va = dict(n_views=args.views, H=args.height, W=args.width, n_points=args.points)
+    n_distinct = 2
+    batches = []
+    for j in range(n_distinct):
+        scans = [synth_scan(1000 * rank + args.batch * j + i, augment=True, device=dev, **va) for i in range(args.batch)]
+        batches.append(scans)
+
+    def device_batch(j):
+        scans = batches[j % n_distinct]
+        return dict(inputs=dict(points=[s['points'] for s in scans], img=[s['img'] for s in scans]),
+                    data_samples=[s['data_sample'] for s in scans])
+
+    def step(j):
+        return model.train_step(device_batch(j), optim)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for j in range(args.warmup):
+        step(j)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    _ffi.launch_counter.update(kernels=0, calls=0, by_name={})
+    SP.CONV_PROFILE['records'].clear()
+    SP.CONV_PROFILE['enabled'] = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for j in range(args.steps):
+        logs = step(args.warmup + j)
+    e1.record()
+    barrier()
+    SP.CONV_PROFILE['enabled'] = False
+    sampler.stop_flag = True
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    launches = _ffi.launch_counter['kernels']
+    value = world * args.batch * args.steps / (ms_total / 1000.0)
+
+    # roofline of the sparse-conv kernel (fwd + dgrad launches of spconv_fwd_kernel) from the events recorded above
+    e = 2 if dtype == torch.bfloat16 else 4
+    tot_bytes = tot_ms = tot_flops = 0.0
+    n_rec = 0
+    wg_bytes = wg_ms = 0.0
+    pair_cache = {}
+    for kind, kmap, cin, cout, _dt, a, b in SP.CONV_PROFILE['records']:
+        if id(kmap) not in pair_cache:
+            pair_cache[id(kmap)] = int(kmap.pairs[2][-1].item())
+        P = pair_cache[id(kmap)]
+        by = P * (cin + cout) * e + 8 * P + kmap.K * cin * cout * e
+        t = a.elapsed_time(b)
+        if kind == 'wgrad':
+            wg_bytes += by
+            wg_ms += t
+        else:
+            tot_bytes += by
+            tot_ms += t
+            tot_flops += 2.0 * P * cin * cout
+            n_rec += 1
+    peak, peak_src = peaks()
+    achieved = tot_bytes / (tot_ms / 1000.0) / 1e9 if tot_ms > 0 else 0.0
+    roofline = {'bound': 'hbm', 'kernel': 'spconv_fwd_kernel (forward + dgrad launches)', 'achieved': achieved,
+                'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'launches_timed': n_rec, 'avg_launch_us': 1000.0 * tot_ms / max(n_rec, 1),
+                'achieved_tflops': tot_flops / (tot_ms / 1000.0) / 1e12 if tot_ms > 0 else 0.0,
+                'share_of_step': tot_ms / ms_total,
+                'wgrad_achieved_gbs': wg_bytes / (wg_ms / 1000.0) / 1e9 if wg_ms > 0 else 0.0,
+                'wgrad_share_of_step': wg_ms / ms_total}
+
+    # end to end: pinned host inputs -> H2D -> train_step -> loss read back, every step
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        for scans in batches:
+            host.append(dict(points=[s['points'].cpu().pin_memory() for s in scans],
+                             img=[s['img'].cpu().pin_memory() for s in scans]))
+        h2d = sum(t.numel() * t.element_size() for t in host[0]['points'] + host[0]['img'])
+
+        def e2e_step(j):
+            hb = host[j % n_distinct]
+            data = dict(inputs=dict(points=hb['points'], img=hb['img']),
+                        data_samples=[s['data_sample'] for s in batches[j % n_distinct]])
+            lg = model.train_step(data, optim)
+            return float(lg['loss'])       # device -> host read of the step's result
+
+        for j in range(max(args.warmup, 3)):
+            e2e_step(j)
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for j in range(args.steps):
+            e2e_step(j)
+        g1.record()
+        barrier()
+        wall = torch.tensor([max(time.perf_counter() - t0, g0.elapsed_time(g1) / 1000.0)], device=dev)
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * args.batch * args.steps / float(wall), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': 4}
+
+    out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+           'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': args.dtype, 'data': 'synthetic',
+           'config': {'workload': f'{args.variant}: mv-3ddet train step, {args.batch} scans/GPU x {args.views} views '
+                                  f'{args.height}x{args.width} RGB-D, {args.points} points/scan, ResNet-50/16 + MinkResNet34 '
+                                  f'+ FCAF3DHeadRotMat, AdamW + clip',
+                      'global_batch': world * args.batch, 'parallelism': f'dp{world}',
+                      'l2': 'per-step working set (340 MB fp32 weights + multi-GB activations) exceeds the 126 MB L2; '
+                            f'{n_distinct} distinct input batches alternate',
+                      'loss': {k: float(v) for k, v in logs.items()}},
+           'clocks': sampler.summary(), 'gpu_launches': launches, 'roofline': roofline, 'impl': 'esb200'}
+    if e2e is not None:
+        out['e2e'] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline(cfg, va, budget_s=25.0, backward=True)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

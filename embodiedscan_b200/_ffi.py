@@ -53,6 +53,18 @@ SIGNATURES = {
 
 _lib = None
 
+# kernels launched per C-ABI call (for bench.py's `gpu_launches`; memsets are not counted)
+KERNELS_PER_CALL = {
+    'esb_voxelize_points': 1, 'esb_coord_unique': 6, 'esb_hash_build': 2, 'esb_hash_lookup': 1, 'esb_kernel_map': 1,
+    'esb_kernel_map_transpose': 2, 'esb_kmap_pairs': 3, 'esb_generative_children': 1, 'esb_spconv_fwd': 1,
+    'esb_spconv_wgrad': 1, 'esb_maxpool_fwd': 1, 'esb_maxpool_bwd': 1, 'esb_norm_fwd': 5, 'esb_norm_apply': 1,
+    'esb_norm_bwd': 2, 'esb_act_fwd': 1, 'esb_paint_fwd': 1, 'esb_paint_bwd': 1, 'esb_fcaf3d_targets': 4,
+    'esb_focal_loss_fwd': 1, 'esb_focal_loss_bwd': 1, 'esb_nms_bev_segmented': 1, 'esb_iou_bev_pairwise': 1,
+    'esb_img_normalize': 1, 'esb_unproject_depth': 3, 'esb_grad_clip_coef': 2, 'esb_adamw_step': 1,
+    'esb_cast_f32_to_bf16': 1, 'esb_spconv_tc_fwd': 1, 'esb_spconv_tc_wgrad': 2,
+}
+launch_counter = {'kernels': 0, 'calls': 0, 'by_name': {}}
+
 
 def exported_symbols():
     return list(SIGNATURES.keys())
@@ -92,6 +104,9 @@ def stream():
 
 
 def call(name, *args):
+    launch_counter['calls'] += 1
+    launch_counter['kernels'] += KERNELS_PER_CALL.get(name, 1)
+    launch_counter['by_name'][name] = launch_counter['by_name'].get(name, 0) + 1
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {last_error()}')

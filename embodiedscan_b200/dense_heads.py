@@ -255,7 +255,8 @@ class FCAF3DHeadRotMat(nn.Module):
             for perm in perms:
                 score = interpolated[perm].squeeze(1)
                 topk = min(len(score), self.pts_prune_threshold)
-                ids = torch.topk(score, topk, sorted=False).indices
+                # torch.topk leaves ties unspecified; frozen rule: descending score, lowest row first among ties
+                ids = torch.sort(score, descending=True, stable=True).indices[:topk]
                 prune_mask[perm[ids]] = True
         return self.pruning(x, prune_mask)
 

@@ -23,6 +23,20 @@ from ._ffi import call, ptr, query, stream
 
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 
+# bench.py switches this on to time every sparse-conv launch with CUDA events on the launching stream
+CONV_PROFILE = {'enabled': False, 'records': []}
+
+
+def _timed_conv_call(kind, kmap, cin, cout, dtype, *args):
+    if not CONV_PROFILE['enabled']:
+        call(*args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(*args)
+    e1.record()
+    CONV_PROFILE['records'].append((kind, kmap, cin, cout, dtype, e0, e1))
+
 
 def _offsets(kernel_size: int, scale: int) -> List[int]:
     """Kernel offsets (x fastest) in voxel units, multiplied by the input tensor stride."""
@@ -227,8 +241,8 @@ class _SparseConv(torch.autograd.Function):
         x = x.contiguous()
         w = weight.detach().to(x.dtype).contiguous()
         y = torch.empty((kmap.n_out, cout), dtype=x.dtype, device=x.device)
-        call('esb_spconv_fwd', ptr(x), ptr(w), ptr(kmap.nbr_out), ptr(y), kmap.n_out, cin, cout, K, 0, 0,
-             _ffi.dtype_code(x.dtype), stream())
+        _timed_conv_call('fwd', kmap, cin, cout, x.dtype, 'esb_spconv_fwd', ptr(x), ptr(w), ptr(kmap.nbr_out), ptr(y),
+                         kmap.n_out, cin, cout, K, 0, 0, _ffi.dtype_code(x.dtype), stream())
         ctx.save_for_backward(x, w)
         ctx.kmap, ctx.cin, ctx.cout, ctx.wshape = kmap, cin, cout, weight.shape
         return y
@@ -243,13 +257,13 @@ class _SparseConv(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty((kmap.n_in, cin), dtype=x.dtype, device=x.device)
             # dgrad = the forward kernel on the input-stationary map with W read transposed
-            call('esb_spconv_fwd', ptr(dy), ptr(w), ptr(kmap.nbr_in), ptr(dx), kmap.n_in, cout, cin, kmap.K, 1, 0, code,
-                 stream())
+            _timed_conv_call('dgrad', kmap, cout, cin, x.dtype, 'esb_spconv_fwd', ptr(dy), ptr(w), ptr(kmap.nbr_in),
+                             ptr(dx), kmap.n_in, cout, cin, kmap.K, 1, 0, code, stream())
         if ctx.needs_input_grad[1]:
             pin, pout, koff, tot = kmap.pairs
             dw = torch.zeros((kmap.K, cin, cout), dtype=torch.float32, device=x.device)
-            call('esb_spconv_wgrad', ptr(x), ptr(dy), ptr(pin), ptr(pout), ptr(koff), ptr(dw), tot, cin, cout, kmap.K,
-                 code, stream())
+            _timed_conv_call('wgrad', kmap, cin, cout, x.dtype, 'esb_spconv_wgrad', ptr(x), ptr(dy), ptr(pin), ptr(pout),
+                             ptr(koff), ptr(dw), tot, cin, cout, kmap.K, code, stream())
             dw = dw.view(ctx.wshape)
         return dx, dw, None, None, None
 

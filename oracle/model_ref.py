@@ -198,6 +198,7 @@ def head_forward(sd, prefix, levels: List[Lvl], voxel_size, n_batch, training, c
     n_lv = len(levels)
     outs = [None] * n_lv
     x = levels[-1]
+    prune_score = None          # (coords, (N,1) max-class logits, stride) of the previous (coarser) output
     for i in range(n_lv - 1, -1, -1):
         if i < n_lv - 1:
             p = f'{prefix}up_block_{i + 1}.'
@@ -208,13 +209,18 @@ def head_forward(sd, prefix, levels: List[Lvl], voxel_size, n_batch, training, c
             ucoords, map_b = S.union(levels[i].coords, y.coords)
             x = Lvl(ucoords, S.union_add(levels[i].F, y.F, map_b, ucoords.shape[0]), y.stride)
             counts = np.bincount(x.coords[:, 0], minlength=n_batch)
-            assert counts.max() <= prune_threshold, 'oracle covers the no-prune regime of the configured thresholds'
+            if counts.max() > prune_threshold:         # _prune (fcaf3d_head.py:1091-1114); identity otherwise
+                with torch.no_grad():
+                    interp = S.features_at_coordinates(prune_score[0], prune_score[1], prune_score[2], x.coords)
+                    keep = S.prune_mask(interp, x.coords[:, 0], n_batch, prune_threshold)
+                x = Lvl(x.coords[keep], x.F[torch.from_numpy(np.nonzero(keep)[0])], x.stride)
         p = f'{prefix}out_block_{i}.'
         o = _conv(sd, p + '0.kernel', x, 3, 1, cache)
         o.F = _elu_bn(sd, p + '1', o.F, training)
         center = o.F @ sd[prefix + 'conv_center.kernel']
         reg = o.F @ sd[prefix + 'conv_reg.kernel']
         cls = o.F @ sd[prefix + 'conv_cls.kernel'] + sd[prefix + 'conv_cls.bias']
+        prune_score = (o.coords, cls.detach().max(dim=1, keepdim=True).values, o.stride)
         dist = torch.exp(reg[:, :6] * sd[f'{prefix}scales.{i}.scale']).clamp(min=1e-3)
         bbox = torch.cat((dist, reg[:, 6:]), 1)
         pts = torch.from_numpy(o.coords[:, 1:]).to(torch.int32) * voxel_size       # int32 * python float -> fp32

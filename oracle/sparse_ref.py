@@ -142,3 +142,39 @@ def union(coords_a: np.ndarray, coords_b: np.ndarray):
 def union_add(fa: torch.Tensor, fb: torch.Tensor, map_b: np.ndarray, n: int) -> torch.Tensor:
     out = torch.cat([fa, fa.new_zeros((n - fa.shape[0], fa.shape[1]))], 0)
     return out.index_add(0, torch.from_numpy(map_b), fb)
+
+
+def features_at_coordinates(coords: np.ndarray, feats: torch.Tensor, ts: int, query: np.ndarray) -> torch.Tensor:
+    """ME SparseTensor.features_at_coordinates (†upstream MinkowskiInterpolation): multilinear interpolation of `feats`
+    (rows at `coords`, lattice spacing `ts`) at integer-valued query coordinates [b,x,y,z]; absent lattice points
+    contribute 0. Corner order k = dx + 2dy + 4dz, accumulated in that order (weights are exact powers of two here)."""
+    q = query.astype(np.int64)
+    base = np.floor_divide(q[:, 1:], ts) * ts
+    frac = torch.from_numpy((q[:, 1:] - base).astype(np.float32) / np.float32(ts))
+    keys = _pack(coords)
+    order = np.argsort(keys)
+    sk = keys[order]
+    out = torch.zeros((q.shape[0], feats.shape[1]), dtype=torch.float32)
+    for k in range(8):
+        d = np.array([k & 1, (k >> 1) & 1, (k >> 2) & 1], dtype=np.int64)
+        w = torch.where(torch.from_numpy(d.astype(bool))[None], frac, 1 - frac).prod(1)
+        nb = np.concatenate([q[:, :1], base + d * ts], 1)
+        qk = _pack(nb)
+        pos = np.minimum(np.searchsorted(sk, qk), sk.shape[0] - 1)
+        hit = sk[pos] == qk
+        rows = torch.from_numpy(np.where(hit, order[pos], 0))
+        out = out + torch.where(torch.from_numpy(hit)[:, None], feats.float()[rows] * w[:, None], torch.zeros(()))
+    return out
+
+
+def prune_mask(scores: torch.Tensor, batch_idx: np.ndarray, n_batch: int, threshold: int) -> np.ndarray:
+    """fcaf3d_head.py:1091-1114: per scan keep the top-`threshold` rows by score. torch.topk leaves ties unspecified;
+    the frozen rule is: descending score, lowest row index first among equal scores."""
+    keep = np.zeros(scores.shape[0], dtype=bool)
+    for b in range(n_batch):
+        sel = np.nonzero(batch_idx == b)[0]
+        sc = scores[torch.from_numpy(sel)].view(-1)
+        k = min(len(sel), threshold)
+        idx = torch.sort(sc, descending=True, stable=True).indices[:k].numpy()
+        keep[sel[idx]] = True
+    return keep
