@@ -206,12 +206,17 @@ def main():
     _ffi.launch_counter.update(kernels=0, calls=0, by_name={})
     SP.CONV_PROFILE['records'].clear()
     SP.CONV_PROFILE['enabled'] = True
+    prof_range = os.environ.get('ESB_CUDA_PROFILER_RANGE') == '1'    # for `ncu --profile-from-start off`
+    if prof_range:
+        torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for j in range(args.steps):
         logs = step(args.warmup + j)
     e1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     SP.CONV_PROFILE['enabled'] = False
     sampler.stop_flag = True
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)

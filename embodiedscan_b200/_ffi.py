@@ -28,6 +28,9 @@ SIGNATURES = {
     'esb_generative_children': ('pqipp', 'i'),
     'esb_spconv_fwd': ('ppppqiiiiiip', 'i'),
     'esb_spconv_wgrad': ('ppppppqiiiip', 'i'),
+    'esb_kmap_tile_masks': ('piqpp', 'i'),
+    'esb_spconv_tc_fwd': ('pppppqiiip', 'i'),
+    'esb_spconv_tc_wgrad': ('ppppppqiiip', 'i'),
     'esb_maxpool_fwd': ('ppppqiiip', 'i'),
     'esb_maxpool_bwd': ('pppqiip', 'i'),
     'esb_norm_fwd': ('ppppiqiippfppfipppip', 'i'),
@@ -61,7 +64,7 @@ KERNELS_PER_CALL = {
     'esb_norm_bwd': 2, 'esb_act_fwd': 1, 'esb_paint_fwd': 1, 'esb_paint_bwd': 1, 'esb_fcaf3d_targets': 4,
     'esb_focal_loss_fwd': 1, 'esb_focal_loss_bwd': 1, 'esb_nms_bev_segmented': 1, 'esb_iou_bev_pairwise': 1,
     'esb_img_normalize': 1, 'esb_unproject_depth': 3, 'esb_grad_clip_coef': 2, 'esb_adamw_step': 1,
-    'esb_cast_f32_to_bf16': 1, 'esb_spconv_tc_fwd': 1, 'esb_spconv_tc_wgrad': 2,
+    'esb_cast_f32_to_bf16': 1, 'esb_spconv_tc_fwd': 1, 'esb_spconv_tc_wgrad': 1, 'esb_kmap_tile_masks': 1,
 }
 launch_counter = {'kernels': 0, 'calls': 0, 'by_name': {}}
 

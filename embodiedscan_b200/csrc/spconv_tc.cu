@@ -1,0 +1,475 @@
+// esb200 — sparse 3D convolution on the 5th-generation tensor cores (tcgen05 + TMEM), bf16 in / fp32 accumulate.
+// The throughput path for ME.MinkowskiConvolution forward / dgrad / wgrad (†upstream MinkowskiEngine; call sites
+// embodiedscan/models/backbones/mink_resnet.py:58-62,104-108, embodiedscan/models/dense_heads/fcaf3d_head.py:919-946).
+//
+// forward / dgrad (spconv_tc_fwd_kernel): output-stationary implicit GEMM. A CTA owns 128 output rows x N_TILE output
+// channels; for every kernel offset k that any row of the tile uses (per-tile bit mask) and every 64-channel slice of
+// Cin it stages
+//     A = the 128 gathered neighbour rows (cp.async 16 B, zero-filled where the neighbour is absent) and
+//     B = W_k^T slice (N_TILE x 64, K-major)
+// into 128B-swizzled shared memory; one elected thread issues tcgen05.mma (M=128, N=N_TILE, K=16) accumulating in
+// TMEM; the epilogue reads TMEM with tcgen05.ld and writes each output row once (no atomics, deterministic).
+// Warp roles: warps 0-3 = gather producers, then epilogue (TMEM lane quadrant = warp id); warp 4 = TMEM allocator +
+// MMA issuer. Full/empty mbarrier ring between producers and the MMA thread; tcgen05.commit releases stages.
+//
+// wgrad (spconv_tc_wgrad_kernel): dW_k = X_k^T dY_k over the compacted pair list of offset k. Both operands are the
+// gathered rows themselves, i.e. MN-major (M = Cin, N = Cout contiguous, reduction over pairs), staged in the
+// canonical MN-major 128B-swizzle layout; split over pair ranges with fp32 atomics into dW.
+//
+// Roofline: pair model bytes = P*(Cin+Cout)*2 + 8P + K*Cin*Cout*2; the gather is L2-fed.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_M = 128;
+constexpr int TC_BK = 64;                      // bf16 elements per smem row = 128 B = one swizzle row
+constexpr int A_STAGE_BYTES = TC_M * 128;      // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 |
+// layout type <<61 (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, majors, N>>3, M>>4
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(uint32_t lo_f32_bits, uint32_t hi_f32_bits) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(lo_f32_bits), __uint_as_float(hi_f32_bits));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// per-tile (128 rows) bit mask of the kernel offsets that have at least one valid neighbour
+__global__ void tile_mask_kernel(const int* __restrict__ nbr, int K, int n, uint32_t* __restrict__ masks) {
+  const int tile = blockIdx.x, r = threadIdx.x;
+  const int row = tile * TC_M + r;
+  uint32_t m = 0;
+  if (row < n)
+    for (int k = 0; k < K; ++k)
+      if (nbr[(long long)k * n + row] >= 0) m |= 1u << k;
+  m = __reduce_or_sync(0xffffffffu, m);
+  __shared__ uint32_t s[4];
+  if ((r & 31) == 0) s[r >> 5] = m;
+  __syncthreads();
+  if (r == 0) masks[tile] = s[0] | s[1] | s[2] | s[3];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward / dgrad
+// ------------------------------------------------------------------------------------------------------------
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(160)
+spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wt,
+                     const int* __restrict__ nbr, const uint32_t* __restrict__ masks, __nv_bfloat16* __restrict__ y,
+                     int n_out, int cin, int cout, int K) {
+  constexpr int B_STAGE_BYTES = N_TILE * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int LAG = STAGES - 2;                 // stages kept in flight per producer thread before it signals
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x;
+  const int n0 = blockIdx.y * N_TILE;
+  const uint32_t mask = masks[tile];
+  const int nchunk = cin / TC_BK;
+  const int total = __popc(mask) * nchunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, N_TILE < 32 ? 32 : N_TILE);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- producers ----------------
+    const int r = threadIdx.x;                       // tile row owned by this thread
+    const int row = tile * TC_M + r;
+    const uint32_t a_row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    const uint32_t sw = (uint32_t)(r & 7);
+    int it = 0;
+    for (uint32_t mk = mask; mk; mk &= mk - 1) {
+      const int k = __ffs(mk) - 1;
+      const int src = row < n_out ? nbr[(long long)k * n_out + row] : -1;
+      const __nv_bfloat16* xrow = x + (long long)(src >= 0 ? src : 0) * cin;
+      const int nbytes = src >= 0 ? 16 : 0;
+      const __nv_bfloat16* wk = wt + ((long long)k * cout + n0) * cin;
+      for (int c = 0; c < nchunk; ++c, ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES) + a_row_off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cp_async16_ca(a_base + ((j ^ sw) << 4), xrow + c * TC_BK + j * 8, nbytes);
+        const uint32_t b_base = smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES);
+#pragma unroll
+        for (int q = 0; q < N_TILE / 16; ++q) {
+          const int idx = q * 128 + r;
+          const int n = idx >> 3, j = idx & 7;
+          cp_async16_cg(b_base + (n >> 3) * 1024 + (n & 7) * 128 + ((j ^ (n & 7)) << 4),
+                        wk + (long long)n * cin + c * TC_BK + j * 8, 16);
+        }
+        cp_async_commit();
+        if (it >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async();
+          mbar_arrive(&full_bar[(it - LAG) % STAGES]);
+        }
+      }
+    }
+    // drain the last LAG stages
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int d = (total > LAG ? total - LAG : 0); d < total; ++d) mbar_arrive(&full_bar[d % STAGES]);
+
+    // ---------------- epilogue ----------------
+    if (total > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+    __nv_bfloat16* yrow = y + (long long)row * cout + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      uint32_t v[32];
+      if (total > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      if (row < n_out) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]);
+          o.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+          o.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]);
+          o.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+          *reinterpret_cast<uint4*>(yrow + c0 + 8 * q) = o;
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---------------- MMA issuer (warp 4) ----------------
+    const uint32_t idesc = make_idesc(TC_M, N_TILE, 0, 0);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&full_bar[s], (it / STAGES) & 1);
+      tc_fence_after();
+      if ((threadIdx.x & 31) == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 16; ++kk) {
+          uint64_t ad = make_desc(a_addr + kk * 32, 16, 1024);
+          uint64_t bd = make_desc(b_addr + kk * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (it == total - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, N_TILE < 32 ? 32 : N_TILE);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad: dW[k] (Cin, Cout) += sum over pairs p of offset k of x[pin[p], :]^T dy[pout[p], :]
+// CTA = (offset k, pair split) x (128-channel slice of Cin) x (N_TILE slice of Cout); reduction dim = pairs (64 / stage)
+// ------------------------------------------------------------------------------------------------------------
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(160)
+spconv_tc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                       const int* __restrict__ pair_in, const int* __restrict__ pair_out,
+                       const int* __restrict__ k_offsets, float* __restrict__ dw, int cin, int cout, int splits) {
+  constexpr int A_BYTES = 64 * 256;              // 64 pairs x 128 channels (2 M-atoms of 64 ch)
+  constexpr int B_BYTES = 64 * N_TILE * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int LAG = STAGES - 2;
+  constexpr int NB_ATOMS = N_TILE / 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int k = blockIdx.x / splits, sp = blockIdx.x - k * splits;
+  const int ci0 = blockIdx.y * 128, co0 = blockIdx.z * N_TILE;
+  const int p_beg = k_offsets[k], p_end = k_offsets[k + 1];
+  const int np = p_end - p_beg;
+  const int per = ((np + splits - 1) / splits + 63) / 64 * 64;
+  const int s_beg = p_beg + sp * per;
+  const int s_end = min(p_end, s_beg + per);
+  const int total = s_end > s_beg ? (s_end - s_beg + 63) / 64 : 0;
+  if (total == 0) return;                          // uniform for the whole CTA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, N_TILE < 32 ? 32 : N_TILE);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int a_ch = min(128, cin - ci0);            // valid channels of the A slice (64 or 128)
+
+  if (warp < 4) {
+    const int t = threadIdx.x;
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+      const int p0 = s_beg + it * 64;
+      const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+      const uint32_t b_base = a_base + A_BYTES;
+      // A: 64 pairs x 16 chunks(16B) ; canonical MN-major SW128: atom(mi, kj) at mi*8192 + kj*1024, row kk%8, chunk^row
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int idx = q * 128 + t;
+        const int kk = idx >> 4, mc = idx & 15;
+        const int p = p0 + kk;
+        const bool ok = p < s_end && mc * 8 < a_ch;
+        const int ri = ok ? pair_in[p] : 0;
+        const uint32_t dst = a_base + (mc >> 3) * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + (((mc & 7) ^ (kk & 7)) << 4);
+        cp_async16_ca(dst, x + (long long)ri * cin + ci0 + mc * 8, ok ? 16 : 0);
+      }
+#pragma unroll
+      for (int q = 0; q < N_TILE / 16; ++q) {
+        const int idx = q * 128 + t;
+        const int kk = idx / (N_TILE / 8), nc = idx % (N_TILE / 8);
+        const int p = p0 + kk;
+        const bool ok = p < s_end;
+        const int ro = ok ? pair_out[p] : 0;
+        const uint32_t dst = b_base + (nc >> 3) * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + (((nc & 7) ^ (kk & 7)) << 4);
+        cp_async16_ca(dst, dy + (long long)ro * cout + co0 + nc * 8, ok ? 16 : 0);
+      }
+      cp_async_commit();
+      if (it >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(&full_bar[(it - LAG) % STAGES]);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int d = (total > LAG ? total - LAG : 0); d < total; ++d) mbar_arrive(&full_bar[d % STAGES]);
+
+    // epilogue: TMEM lane = ci (within the 128 slice), column = co
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int ci = ci0 + threadIdx.x;
+    float* dwrow = dw + ((long long)k * cin + ci) * cout + co0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (ci < cin) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(dwrow + c0 + i, __uint_as_float(v[i]));
+      }
+    }
+    tc_fence_before();
+  } else {
+    const uint32_t idesc = make_idesc(128, N_TILE, 1, 1);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&full_bar[s], (it / STAGES) & 1);
+      tc_fence_after();
+      if ((threadIdx.x & 31) == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {           // 16 pairs per MMA = two 8-row K groups = 2048 B
+          uint64_t ad = make_desc(a_addr + kk * 2048, 8192, 1024);
+          uint64_t bd = make_desc(b_addr + kk * 2048, 8192, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (it == total - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, N_TILE < 32 ? 32 : N_TILE);
+  }
+  (void)NB_ATOMS;
+}
+
+template <int N_TILE, int STAGES>
+int launch_fwd(const void* x, const void* wt, const int* nbr, const unsigned* masks, void* y, long long n_out, int cin,
+               int cout, int K, cudaStream_t stream) {
+  size_t smem = (size_t)STAGES * (A_STAGE_BYTES + N_TILE * 128) + 1024 + 256;
+  auto kern = spconv_tc_fwd_kernel<N_TILE, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { esb_set_error("spconv_tc_fwd: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
+  dim3 grid(esb_div_up(n_out, TC_M), cout / N_TILE);
+  kern<<<grid, 160, smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)wt, nbr, masks, (__nv_bfloat16*)y,
+                                    (int)n_out, cin, cout, K);
+  return ESB_OK;
+}
+
+template <int N_TILE, int STAGES>
+int launch_wgrad(const void* x, const void* dy, const int* pin, const int* pout, const int* koff, float* dw, int cin,
+                 int cout, int K, int splits, cudaStream_t stream) {
+  size_t smem = (size_t)STAGES * (64 * 256 + 64 * N_TILE * 2) + 1024 + 256;
+  auto kern = spconv_tc_wgrad_kernel<N_TILE, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { esb_set_error("spconv_tc_wgrad: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
+  dim3 grid(K * splits, esb_div_up(cin, 128), cout / N_TILE);
+  kern<<<grid, 160, smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, pin, pout, koff, dw, cin, cout,
+                                    splits);
+  return ESB_OK;
+}
+
+}  // namespace
+
+// masks: ceil(n/128) uint32, bit k set when any row of the tile has a neighbour through offset k
+extern "C" int esb_kmap_tile_masks(const int* nbr, int K, long long n, unsigned* masks, void* stream) {
+  ESB_CHECK_ARG(K >= 1 && K <= 32, "esb_kmap_tile_masks: K must be in [1,32]");
+  if (n == 0) return ESB_OK;
+  tile_mask_kernel<<<esb_div_up(n, TC_M), 128, 0, (cudaStream_t)stream>>>(nbr, K, (int)n, masks);
+  ESB_CUDA_LAUNCH_CHECK("tile_mask_kernel");
+  return ESB_OK;
+}
+
+// bf16 tensor-core forward / dgrad. x (n_in,cin) ; wt (K,cout,cin) [W_k^T, reduction dim contiguous] ; nbr (K,n_out);
+// masks from esb_kmap_tile_masks(nbr) ; y (n_out,cout). Requires cin % 64 == 0 and cout % 64 == 0.
+extern "C" int esb_spconv_tc_fwd(const void* x, const void* wt, const int* nbr, const unsigned* masks, void* y,
+                                 long long n_out, int cin, int cout, int K, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESB_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0 && cin > 0 && cout > 0, "esb_spconv_tc_fwd: channels must be multiples of 64");
+  ESB_CHECK_ARG(K >= 1 && K <= 27, "esb_spconv_tc_fwd: K must be in [1,27]");
+  if (n_out == 0) return ESB_OK;
+  int rc;
+  // wide tiles amortise the gather; narrow tiles when there are too few row tiles to fill 148 SMs
+  long long row_tiles = (n_out + TC_M - 1) / TC_M;
+  if (cout % 256 == 0 && row_tiles * (cout / 256) >= 148)
+    rc = launch_fwd<256, 4>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream);
+  else if (cout % 128 == 0 && row_tiles * (cout / 128) >= 148)
+    rc = launch_fwd<128, 3>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream);
+  else
+    rc = launch_fwd<64, 4>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream);
+  if (rc != ESB_OK) return rc;
+  ESB_CUDA_LAUNCH_CHECK("spconv_tc_fwd_kernel");
+  return ESB_OK;
+}
+
+// bf16 tensor-core wgrad over pair lists; dw (K,cin,cout) fp32, zeroed by the caller (atomic accumulation over splits).
+extern "C" int esb_spconv_tc_wgrad(const void* x, const void* dy, const int* pair_in, const int* pair_out,
+                                   const int* k_offsets, float* dw, long long n_pairs_hint, int cin, int cout, int K,
+                                   void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESB_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0 && cin > 0 && cout > 0, "esb_spconv_tc_wgrad: channels must be multiples of 64");
+  int n_tile = (cout % 128 == 0) ? 128 : 64;
+  int ctas_per_split = K * esb_div_up(cin, 128) * (cout / n_tile);
+  long long per_k = n_pairs_hint / K + 1;
+  int splits = (int)(2 * 148 / ctas_per_split);
+  int max_by_pairs = (int)(per_k / 512) + 1;
+  if (splits > max_by_pairs) splits = max_by_pairs;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  int rc = n_tile == 128 ? launch_wgrad<128, 3>(x, dy, pair_in, pair_out, k_offsets, dw, cin, cout, K, splits, stream)
+                         : launch_wgrad<64, 4>(x, dy, pair_in, pair_out, k_offsets, dw, cin, cout, K, splits, stream);
+  if (rc != ESB_OK) return rc;
+  ESB_CUDA_LAUNCH_CHECK("spconv_tc_wgrad_kernel");
+  return ESB_OK;
+}

@@ -23,6 +23,10 @@ from ._ffi import call, ptr, query, stream
 
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 
+# bf16 sparse convolutions run on tcgen05 tensor cores when the channel counts tile (multiples of 64)
+USE_TENSOR_CORES = True
+USE_TC_WGRAD = True
+
 # bench.py switches this on to time every sparse-conv launch with CUDA events on the launching stream
 CONV_PROFILE = {'enabled': False, 'records': []}
 
@@ -99,6 +103,7 @@ class KernelMap:
         self.nbr_out, self.n_in, self.n_out, self.K = nbr_out, n_in, n_out, K
         self._nbr_in = None
         self._pairs = None
+        self._masks = {}
 
     @property
     def nbr_in(self):
@@ -107,6 +112,15 @@ class KernelMap:
             call('esb_kernel_map_transpose', ptr(self.nbr_out), self.K, self.n_out, self.n_in, ptr(t), stream())
             self._nbr_in = t
         return self._nbr_in
+
+    def tile_masks(self, side: str):
+        """Per 128-row tile bit mask of used kernel offsets, for nbr_out ('out') or nbr_in ('in')."""
+        if side not in self._masks:
+            nbr, n = (self.nbr_out, self.n_out) if side == 'out' else (self.nbr_in, self.n_in)
+            m = torch.zeros(max((n + 127) // 128, 1), dtype=torch.int32, device=nbr.device)
+            call('esb_kmap_tile_masks', ptr(nbr), self.K, n, ptr(m), stream())
+            self._masks[side] = m
+        return self._masks[side]
 
     @property
     def pairs(self):
@@ -241,10 +255,16 @@ class _SparseConv(torch.autograd.Function):
         x = x.contiguous()
         w = weight.detach().to(x.dtype).contiguous()
         y = torch.empty((kmap.n_out, cout), dtype=x.dtype, device=x.device)
-        _timed_conv_call('fwd', kmap, cin, cout, x.dtype, 'esb_spconv_fwd', ptr(x), ptr(w), ptr(kmap.nbr_out), ptr(y),
-                         kmap.n_out, cin, cout, K, 0, 0, _ffi.dtype_code(x.dtype), stream())
+        tc = USE_TENSOR_CORES and x.dtype == torch.bfloat16 and cin % 64 == 0 and cout % 64 == 0
+        if tc:
+            wt = w.view(K, cin, cout).transpose(1, 2).contiguous()          # W_k^T: reduction dim contiguous
+            _timed_conv_call('fwd', kmap, cin, cout, x.dtype, 'esb_spconv_tc_fwd', ptr(x), ptr(wt), ptr(kmap.nbr_out),
+                             ptr(kmap.tile_masks('out')), ptr(y), kmap.n_out, cin, cout, K, stream())
+        else:
+            _timed_conv_call('fwd', kmap, cin, cout, x.dtype, 'esb_spconv_fwd', ptr(x), ptr(w), ptr(kmap.nbr_out),
+                             ptr(y), kmap.n_out, cin, cout, K, 0, 0, _ffi.dtype_code(x.dtype), stream())
         ctx.save_for_backward(x, w)
-        ctx.kmap, ctx.cin, ctx.cout, ctx.wshape = kmap, cin, cout, weight.shape
+        ctx.kmap, ctx.cin, ctx.cout, ctx.wshape, ctx.tc = kmap, cin, cout, weight.shape, tc
         return y
 
     @staticmethod
@@ -257,13 +277,21 @@ class _SparseConv(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty((kmap.n_in, cin), dtype=x.dtype, device=x.device)
             # dgrad = the forward kernel on the input-stationary map with W read transposed
-            _timed_conv_call('dgrad', kmap, cout, cin, x.dtype, 'esb_spconv_fwd', ptr(dy), ptr(w), ptr(kmap.nbr_in),
-                             ptr(dx), kmap.n_in, cout, cin, kmap.K, 1, 0, code, stream())
+            if ctx.tc:   # (K,cin,cout) already is the K-major B operand of the transposed problem
+                _timed_conv_call('dgrad', kmap, cout, cin, x.dtype, 'esb_spconv_tc_fwd', ptr(dy), ptr(w), ptr(kmap.nbr_in),
+                                 ptr(kmap.tile_masks('in')), ptr(dx), kmap.n_in, cout, cin, kmap.K, stream())
+            else:
+                _timed_conv_call('dgrad', kmap, cout, cin, x.dtype, 'esb_spconv_fwd', ptr(dy), ptr(w), ptr(kmap.nbr_in),
+                                 ptr(dx), kmap.n_in, cout, cin, kmap.K, 1, 0, code, stream())
         if ctx.needs_input_grad[1]:
             pin, pout, koff, tot = kmap.pairs
             dw = torch.zeros((kmap.K, cin, cout), dtype=torch.float32, device=x.device)
-            _timed_conv_call('wgrad', kmap, cin, cout, x.dtype, 'esb_spconv_wgrad', ptr(x), ptr(dy), ptr(pin), ptr(pout),
-                             ptr(koff), ptr(dw), tot, cin, cout, kmap.K, code, stream())
+            if ctx.tc and USE_TC_WGRAD:
+                _timed_conv_call('wgrad', kmap, cin, cout, x.dtype, 'esb_spconv_tc_wgrad', ptr(x), ptr(dy), ptr(pin),
+                                 ptr(pout), ptr(koff), ptr(dw), tot, cin, cout, kmap.K, stream())
+            else:
+                _timed_conv_call('wgrad', kmap, cin, cout, x.dtype, 'esb_spconv_wgrad', ptr(x), ptr(dy), ptr(pin),
+                                 ptr(pout), ptr(koff), ptr(dw), tot, cin, cout, kmap.K, code, stream())
             dw = dw.view(ctx.wshape)
         return dx, dw, None, None, None
 

@@ -58,6 +58,13 @@ int esb_spconv_fwd(const void* x, const void* w, const int* nbr, void* y, long l
 int esb_spconv_wgrad(const void* x, const void* dy, const int* pair_in, const int* pair_out, const int* k_offsets,
                      float* dw, long long n_pairs_hint, int cin, int cout, int K, int dtype, void* stream);
 
+/* bf16 tensor-core (tcgen05/TMEM) path of the same operator; wt = W_k^T (K,cout,cin); masks from esb_kmap_tile_masks */
+int esb_kmap_tile_masks(const int* nbr, int K, long long n, unsigned* masks, void* stream);
+int esb_spconv_tc_fwd(const void* x, const void* wt, const int* nbr, const unsigned* masks, void* y, long long n_out,
+                      int cin, int cout, int K, void* stream);
+int esb_spconv_tc_wgrad(const void* x, const void* dy, const int* pair_in, const int* pair_out, const int* k_offsets,
+                        float* dw, long long n_pairs_hint, int cin, int cout, int K, void* stream);
+
 /* ---- pooling / normalisation / activation (ME.MinkowskiMaxPooling, InstanceNorm, BatchNorm, ReLU, ELU;
  * mink_resnet.py:64-69, fcaf3d_head.py:923,942,947) -------------------------------------------------------------- */
 int esb_maxpool_fwd(const void* x, const int* nbr, void* y, int* arg, long long n_out, int C, int K, int dtype,

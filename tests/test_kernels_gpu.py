@@ -105,7 +105,9 @@ def test_generative_and_union_bit_exact():
 @pytest.mark.parametrize('cin,cout,ksize,stride,dtype', [
     (3, 64, 3, 2, torch.float32), (64, 64, 3, 1, torch.float32), (64, 128, 3, 2, torch.float32),
     (128, 128, 3, 1, torch.float32), (64, 128, 1, 2, torch.float32), (96, 40, 3, 1, torch.float32),
-    (64, 64, 3, 1, torch.bfloat16), (128, 256, 3, 2, torch.bfloat16)])
+    (64, 64, 3, 1, torch.bfloat16), (128, 256, 3, 2, torch.bfloat16), (128, 128, 3, 1, torch.bfloat16),
+    (256, 512, 3, 2, torch.bfloat16), (512, 512, 3, 1, torch.bfloat16), (1024, 128, 3, 1, torch.bfloat16),
+    (64, 128, 1, 2, torch.bfloat16), (192, 64, 3, 1, torch.bfloat16)])
 def test_spconv_fwd_bwd(cin, cout, ksize, stride, dtype):
     from embodiedscan_b200 import sparse as SP
     from oracle import sparse_ref as R
@@ -134,7 +136,8 @@ def test_spconv_fwd_bwd(cin, cout, ksize, stride, dtype):
     y = conv(SP.SparseTensor(xd, coordinate_map_key=key, coordinate_manager=mgr))
     assert np.array_equal(y.C.cpu().numpy().astype(np.int64), out_c)
     y.F.backward(gy.to(_dev(), dtype))
-    tol = RTOL if dtype == torch.float32 else 2e-2     # bf16 storage: 8-bit mantissa outputs
+    # bf16 storage (8-bit mantissa outputs); the tcgen05 path (channels % 64 == 0) accumulates in fp32 TMEM
+    tol = RTOL if dtype == torch.float32 else 2e-2
     _close(y.F, yr, tol, 'fwd')
     _close(xd.grad, xr.grad, tol, 'dgrad')
     _close(conv.kernel.grad, wr.grad.view_as(conv.kernel), tol, 'wgrad')
