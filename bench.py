@@ -28,6 +28,14 @@ METRIC = 'training scans/sec mv-3ddet 20-view (ResNet-50/16 + MinkResNet34, 480x
 UNIT = 'scans/s'
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    if int(os.environ.get('RANK', 0)) == 0:
+        print(f'[bench +{time.time() - _T0:6.1f}s] {msg}', file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -114,7 +122,7 @@ def cpu_baseline(cfg, variant_args, budget_s=30.0, backward=True, max_steps=None
     from embodiedscan_b200 import MODELS
     from embodiedscan_b200.synth import synth_scan
     torch.manual_seed(0)
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)     # torch-CPU stops scaling (and thrashes on tiny ops) beyond ~32 threads
     torch.set_num_threads(cores)
     sd = {k: v.detach().clone().float() for k, v in MODELS.build(cfg).state_dict().items()}
     scan = synth_scan(0, device='cpu', **variant_args)
@@ -130,6 +138,21 @@ def cpu_baseline(cfg, variant_args, budget_s=30.0, backward=True, max_steps=None
                       ' (no optimiser step), oracle restatement in torch-CPU fp32 — the reference stack '
                       '(MinkowskiEngine / mmcv / pytorch3d / mmdet / mmengine) is not installable here',
             'seconds': el}
+
+
+def cpu_baseline_subprocess(args, timeout_s=200):
+    """Run the CPU port in a child process so a slow host cannot stall the GPU measurement."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2', '--warmup', '0',
+           '--views', str(args.views), '--height', str(args.height), '--width', str(args.width), '--points',
+           str(args.points), '--variant', args.variant]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', RANK='0', WORLD_SIZE='1')
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        line = [l for l in p.stdout.splitlines() if l.startswith('{')][-1]
+        return json.loads(line)['cpu_baseline']
+    except Exception as e:  # noqa
+        return {'value': None, 'unit': UNIT, 'cores': min(os.cpu_count() or 1, 32), 'kind': 'port',
+                'sample': f'unavailable: {type(e).__name__} within {timeout_s}s'}
 
 
 def run_reference(args):
@@ -198,8 +221,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log(f'model + {n_distinct} batches ready')
     for j in range(args.warmup):
         step(j)
+        log(f'warmup step {j} done')
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -219,6 +244,7 @@ def main():
         torch.cuda.profiler.stop()
     SP.CONV_PROFILE['enabled'] = False
     sampler.stop_flag = True
+    log('timed region done')
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -272,9 +298,11 @@ def main():
             lg = model.train_step(data, optim)
             return float(lg['loss'])       # device -> host read of the step's result
 
+        log('e2e warmup')
         for j in range(max(args.warmup, 3)):
             e2e_step(j)
         barrier()
+        log('e2e timed')
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
@@ -302,7 +330,8 @@ def main():
     if e2e is not None:
         out['e2e'] = e2e
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_baseline(cfg, va, budget_s=25.0, backward=True)
+        log('cpu baseline (oracle port, subprocess with a hard timeout)')
+        out['cpu_baseline'] = cpu_baseline_subprocess(args, timeout_s=200)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
