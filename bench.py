@@ -51,6 +51,7 @@ def parse():
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--torch-profile', default='', help='write a torch.profiler kernel table of 2 steps to this path')
     return ap.parse_args()
 
 
@@ -63,33 +64,57 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region, sampled in-process through NVML (spawning nvidia-smi every
+    200 ms perturbs the measurement); falls back to one nvidia-smi query per second when pynvml is unavailable."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.index, self.stop_flag, self.sm, self.reasons_seen, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            phys = index
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                try:
+                    phys = int(vis.split(',')[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def run(self):
-        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
+                if self.nv is not None:
+                    nv = self.nv
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    for name, bit in (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40),
+                                      ('sw_power_cap', 0x4)):
+                        if r & bit:
+                            self.reasons_seen.add(name)
+                    time.sleep(0.05)
+                else:
+                    q = 'clocks.sm,clocks.max.sm'
+                    out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
+                                          '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                         timeout=5).stdout.strip().split(',')
+                    self.sm.append(float(out[0]))
+                    self.max_mhz = float(out[1])
+                    time.sleep(1.0)
             except Exception:
-                pass
-            time.sleep(0.2)
+                time.sleep(0.2)
 
     def summary(self):
-        if not self.rows:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons,
-                'samples': len(self.rows)}
+        if not self.sm:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unavailable']}
+        sm = sorted(self.sm)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons_seen),
+                'samples': len(sm), 'source': 'nvml' if self.nv is not None else 'nvidia-smi'}
 
 
 def _trainable(k, v):
@@ -222,6 +247,20 @@ def main():
         torch.cuda.synchronize()
 
     log(f'model + {n_distinct} batches ready')
+    if args.torch_profile:
+        from torch.profiler import ProfilerActivity, profile
+        for j in range(3):
+            step(j)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for j in range(2):
+                step(j)
+            torch.cuda.synchronize()
+        with open(args.torch_profile, 'w') as f:
+            f.write(prof.key_averages().table(sort_by='cuda_time_total', row_limit=60, max_name_column_width=70))
+            f.write('\n\n')
+            f.write(prof.key_averages().table(sort_by='self_cpu_time_total', row_limit=40, max_name_column_width=70))
+        log('torch profile written')
     for j in range(args.warmup):
         step(j)
         log(f'warmup step {j} done')

@@ -48,29 +48,29 @@ __device__ __forceinline__ float centerness_of(const FaceDist& f) {
   return __fsqrt_rn(t);
 }
 
-// counts[l*Ng + b] = number of level-l points inside box b
-__global__ void count_inside_kernel(const float* __restrict__ pts, const int* __restrict__ level_off, int L, int Np,
-                                    const float* __restrict__ boxes, const float* __restrict__ rneg, int Ng,
-                                    int* __restrict__ counts) {
-  int b = blockIdx.y;
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  int inside = 0, lvl = 0;
-  if (p < Np) {
-    FaceDist f = face_distances(boxes + b * 9, rneg + b * 9, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
-    inside = inside_box(f);
-    while (lvl + 1 < L && p >= level_off[lvl + 1]) ++lvl;
-  }
-  // a block rarely spans more than one level boundary: aggregate per warp by level match with lane 0's level
-  unsigned m = __ballot_sync(0xffffffffu, inside);
-  if (m) {
-    int l0 = __shfl_sync(0xffffffffu, lvl, 0);
-    unsigned same = __ballot_sync(0xffffffffu, lvl == l0);
-    if ((threadIdx.x & 31) == 0 && (m & same)) atomicAdd(&counts[l0 * Ng + b], __popc(m & same));
-    if (inside && lvl != l0) atomicAdd(&counts[lvl * Ng + b], 1);
-  }
+// All scans of the batch in one pipeline: points of a level are rows of every scan in natural (map) order,
+// pt_batch[p] names the scan; boxes of scan b are rows [box_off[b], box_off[b+1]) of the concatenated box arrays.
+__device__ __forceinline__ int level_of(const int* __restrict__ level_off, int L, int p) {
+  int lvl = 0;
+  while (lvl + 1 < L && p >= level_off[lvl + 1]) ++lvl;
+  return lvl;
 }
 
-// best_level[b] per fcaf3d_head.py:1628-1634
+// counts[l*NgT + g] = number of level-l points of g's scan inside box g
+__global__ void count_inside_kernel(const float* __restrict__ pts, const int* __restrict__ level_off, int L, int Np,
+                                    const int* __restrict__ pt_batch, const float* __restrict__ boxes,
+                                    const float* __restrict__ rneg, const int* __restrict__ box_off, int NgT,
+                                    int* __restrict__ counts) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Np) return;
+  int b = pt_batch ? pt_batch[p] : 0;
+  int g = box_off[b] + blockIdx.y;
+  if (g >= box_off[b + 1]) return;
+  FaceDist f = face_distances(boxes + g * 9, rneg + g * 9, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
+  if (inside_box(f)) atomicAdd(&counts[level_of(level_off, L, p) * NgT + g], 1);
+}
+
+// best_level[g] per fcaf3d_head.py:1628-1634
 __global__ void best_level_kernel(const int* __restrict__ counts, int L, int Ng, int assign_thr, int* __restrict__ best) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= Ng) return;
@@ -82,51 +82,69 @@ __global__ void best_level_kernel(const int* __restrict__ counts, int L, int Ng,
   best[b] = first < 0 ? L - 1 : lower_index;
 }
 
-// top[b] = (k+1)-th largest of the masked centerness column of box b (fcaf3d_head.py:1643-1650), k+1 = kth.
-// One CTA per box; candidates live only in the box's best level, all other entries are -1.
+// top[g] = (k+1)-th largest of the masked centerness column of box g (fcaf3d_head.py:1643-1650), k+1 = kth.
+// One CTA per box. Candidates (points of g's scan in g's best level, inside the box) are compacted into shared memory in
+// ONE pass over the level; the kth rounds of "next largest in (value desc, index asc) order" then run over that list.
+// Boxes with more than TOPK_CAP candidates fall back to rescanning the level each round.
+constexpr int TOPK_CAP = 4096;
+
 __global__ void __launch_bounds__(256)
-topk_threshold_kernel(const float* __restrict__ pts, const int* __restrict__ level_off, int Np,
-                      const float* __restrict__ boxes, const float* __restrict__ rneg, const int* __restrict__ best,
-                      int kth, float* __restrict__ top) {
+topk_threshold_kernel(const float* __restrict__ pts, const int* __restrict__ level_off, const int* __restrict__ pt_batch,
+                      const int* __restrict__ n_pts_of_scan, const float* __restrict__ boxes,
+                      const float* __restrict__ rneg, const int* __restrict__ box_off, int B,
+                      const int* __restrict__ best, int kth, float* __restrict__ top) {
+  __shared__ float c_val[TOPK_CAP];
+  __shared__ int c_idx[TOPK_CAP];
   __shared__ float s_val[256];
   __shared__ int s_idx[256];
   __shared__ float prev_v;
   __shared__ int prev_i;
   __shared__ int n_cand;
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int lvl = best[b];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  int scan = 0;
+  while (scan + 1 < B && g >= box_off[scan + 1]) ++scan;
+  const int lvl = best[g];
   const int p_beg = level_off[lvl], p_end = level_off[lvl + 1];
-  const float* box = boxes + b * 9;
-  const float* R = rneg + b * 9;
-  int k_eff = min(kth, Np);
+  const float* box = boxes + g * 9;
+  const float* R = rneg + g * 9;
+  const int k_eff = min(kth, n_pts_of_scan[scan]);
   if (tid == 0) { prev_v = INFINITY; prev_i = -1; n_cand = 0; }
   __syncthreads();
-  {  // count candidates
-    int c = 0;
-    for (int p = p_beg + tid; p < p_end; p += 256) {
-      FaceDist f = face_distances(box, R, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
-      c += inside_box(f) ? 1 : 0;
-    }
-    if (c) atomicAdd(&n_cand, c);
+  for (int p = p_beg + tid; p < p_end; p += 256) {
+    if (pt_batch && pt_batch[p] != scan) continue;
+    FaceDist f = face_distances(box, R, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
+    if (!inside_box(f)) continue;
+    int slot = atomicAdd(&n_cand, 1);
+    if (slot < TOPK_CAP) { c_val[slot] = centerness_of(f); c_idx[slot] = p; }
   }
   __syncthreads();
-  if (n_cand < k_eff) {  // the k-th largest entry is one of the -1 fillers
-    if (tid == 0) top[b] = -1.f;
+  const int nc = n_cand;
+  if (nc < k_eff) {  // the k-th largest entry is one of the -1 fillers
+    if (tid == 0) top[g] = -1.f;
     return;
   }
-  // k_eff rounds of "largest element strictly after (prev_v, prev_i) in (value desc, index asc) order"
+  const bool in_smem = nc <= TOPK_CAP;
   for (int round = 0; round < k_eff; ++round) {
     float bv = -INFINITY;
     int bi = -1;
-    float pv = prev_v;
-    int pi = prev_i;
-    for (int p = p_beg + tid; p < p_end; p += 256) {
-      FaceDist f = face_distances(box, R, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
-      if (!inside_box(f)) continue;
-      float v = centerness_of(f);
-      bool after = (v < pv) || (v == pv && p > pi);
-      if (!after) continue;
-      if (bi < 0 || v > bv || (v == bv && p < bi)) { bv = v; bi = p; }
+    const float pv = prev_v;
+    const int pi = prev_i;
+    if (in_smem) {
+      for (int c = tid; c < nc; c += 256) {
+        float v = c_val[c];
+        int p = c_idx[c];
+        bool after = (v < pv) || (v == pv && p > pi);
+        if (after && (bi < 0 || v > bv || (v == bv && p < bi))) { bv = v; bi = p; }
+      }
+    } else {
+      for (int p = p_beg + tid; p < p_end; p += 256) {
+        if (pt_batch && pt_batch[p] != scan) continue;
+        FaceDist f = face_distances(box, R, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
+        if (!inside_box(f)) continue;
+        float v = centerness_of(f);
+        bool after = (v < pv) || (v == pv && p > pi);
+        if (after && (bi < 0 || v > bv || (v == bv && p < bi))) { bv = v; bi = p; }
+      }
     }
     s_val[tid] = bv;
     s_idx[tid] = bi;
@@ -143,38 +161,56 @@ topk_threshold_kernel(const float* __restrict__ pts, const int* __restrict__ lev
     if (tid == 0) { prev_v = s_val[0]; prev_i = s_idx[0]; }
     __syncthreads();
   }
-  if (tid == 0) top[b] = prev_v;
+  if (tid == 0) top[g] = prev_v;
 }
 
-// per point: min-volume box among (inside & best level & centerness > top[b]) ; first index wins ties.
+// number of points of each scan (torch.topk's `min(k+1, len(centerness))` uses the scan's total point count)
+__global__ void count_scan_points_kernel(const int* __restrict__ pt_batch, int Np, int* __restrict__ n_pts_of_scan) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Np) return;
+  atomicAdd(&n_pts_of_scan[pt_batch ? pt_batch[p] : 0], 1);
+}
+
+// per point: min-volume box among (inside & best level & centerness > top[g]) over the boxes of its scan;
+// first index wins ties.
 __global__ void assign_kernel(const float* __restrict__ pts, const int* __restrict__ level_off, int L, int Np,
-                              const float* __restrict__ boxes, const float* __restrict__ rneg,
-                              const long long* __restrict__ labels, int Ng, const int* __restrict__ best,
+                              const int* __restrict__ pt_batch, const float* __restrict__ boxes,
+                              const float* __restrict__ rneg, const long long* __restrict__ labels,
+                              const int* __restrict__ box_off, const int* __restrict__ best,
                               const float* __restrict__ top, float* __restrict__ center_t, float* __restrict__ bbox_t,
                               long long* __restrict__ cls_t, int* __restrict__ box_idx) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Np) return;
-  int lvl = 0;
-  while (lvl + 1 < L && p >= level_off[lvl + 1]) ++lvl;
+  const int lvl = level_of(level_off, L, p);
+  const int b = pt_batch ? pt_batch[p] : 0;
+  const int g_beg = box_off[b], g_end = box_off[b + 1];
   float px = pts[3 * p], py = pts[3 * p + 1], pz = pts[3 * p + 2];
   const float FMAX = 1e8f;
   float min_vol = FMAX;
-  int min_ind = 0;
+  int min_ind = g_beg;
   float cent_sel = -1.f, cent0 = -1.f;
-  for (int b = 0; b < Ng; ++b) {
-    const float* box = boxes + b * 9;
-    FaceDist f = face_distances(box, rneg + b * 9, px, py, pz);
+  for (int g = g_beg; g < g_end; ++g) {
+    const float* box = boxes + g * 9;
+    FaceDist f = face_distances(box, rneg + g * 9, px, py, pz);
     bool in = inside_box(f);
-    bool lv = best[b] == lvl;
+    bool lv = best[g] == lvl;
     float c = (in && lv) ? centerness_of(f) : -1.f;
-    if (b == 0) cent0 = c;
-    if (in && lv && c > top[b]) {
+    if (g == g_beg) cent0 = c;
+    if (in && lv && c > top[g]) {
       float vol = __fmul_rn(__fmul_rn(box[3], box[4]), box[5]);
-      if (vol < min_vol) { min_vol = vol; min_ind = b; cent_sel = c; }
+      if (vol < min_vol) { min_vol = vol; min_ind = g; cent_sel = c; }
     }
   }
   bool pos = min_vol < FMAX;
-  // negatives inherit argmin over an all-1e8 row = box 0 (reference behaviour; values unused by the loss)
+  if (g_end == g_beg) {  // scan without boxes: pseudo targets (fcaf3d_head.py:1601-1605)
+    center_t[p] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) bbox_t[p * 9 + j] = 0.f;
+    cls_t[p] = -1;
+    if (box_idx) box_idx[p] = -1;
+    return;
+  }
+  // negatives inherit argmin over an all-1e8 row = the scan's first box (reference behaviour; unused by the loss)
   center_t[p] = pos ? cent_sel : cent0;
 #pragma unroll
   for (int j = 0; j < 9; ++j) bbox_t[p * 9 + j] = boxes[min_ind * 9 + j];
@@ -187,7 +223,7 @@ __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x
 
 template <typename T>
 __global__ void focal_fwd_kernel(const T* __restrict__ logits, const long long* __restrict__ target, long long n, int C,
-                                 float gamma, float alpha, float* __restrict__ loss_sum) {
+                                 float gamma, float alpha, const float* __restrict__ row_w, float* __restrict__ loss_sum) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   float l = 0.f;
   if (t < n * C) {
@@ -198,6 +234,7 @@ __global__ void focal_fwd_kernel(const T* __restrict__ logits, const long long* 
       l = -alpha * powf(1.f - p, gamma) * logf(fmaxf(p, 1.17549435e-38f));
     else
       l = -(1.f - alpha) * powf(p, gamma) * logf(fmaxf(1.f - p, 1.17549435e-38f));
+    if (row_w) l *= row_w[r];
   }
   l = esb_warp_sum(l);
   __shared__ float red[8];
@@ -213,7 +250,8 @@ __global__ void focal_fwd_kernel(const T* __restrict__ logits, const long long* 
 // grad[t] = scale[0] * dloss/dlogit ; scale is a device scalar (grad_out / avg_factor) so no host sync is needed
 template <typename T>
 __global__ void focal_bwd_kernel(const T* __restrict__ logits, const long long* __restrict__ target, long long n, int C,
-                                 float gamma, float alpha, const float* __restrict__ scale, T* __restrict__ grad) {
+                                 float gamma, float alpha, const float* __restrict__ row_w,
+                                 const float* __restrict__ scale, T* __restrict__ grad) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n * C) return;
   long long r = t / C;
@@ -224,67 +262,79 @@ __global__ void focal_bwd_kernel(const T* __restrict__ logits, const long long* 
     g = -alpha * powf(1.f - p, gamma) * (1.f - p - gamma * p * logf(fmaxf(p, 1.17549435e-38f)));
   else
     g = -(1.f - alpha) * powf(p, gamma) * (gamma * (1.f - p) * logf(fmaxf(1.f - p, 1.17549435e-38f)) - p);
-  grad[t] = esb_from_float<T>(g * scale[0]);
+  grad[t] = esb_from_float<T>(g * scale[0] * (row_w ? row_w[r] : 1.f));
 }
 
 }  // namespace
 
-extern "C" size_t esb_fcaf3d_targets_workspace_bytes(int L, int Ng) {
-  return esb_align((size_t)L * Ng * 4) + 2 * esb_align((size_t)Ng * 4);
+extern "C" size_t esb_fcaf3d_targets_workspace_bytes(int L, int NgT, int B) {
+  return esb_align((size_t)L * NgT * 4) + 2 * esb_align((size_t)NgT * 4) + esb_align((size_t)B * 4);
 }
 
-// points (Np,3) fp32 concatenated level by level (level_off: L+1 device ints); boxes (Ng,9); rneg (Ng,9);
-// labels (Ng) int64. Outputs: center_t (Np), bbox_t (Np,9), cls_t (Np) int64 (-1 = background), box_idx (Np) or NULL.
-extern "C" int esb_fcaf3d_targets(const float* points, const int* level_off, int L, int Np, const float* boxes,
-                                  const float* rneg, const long long* labels, int Ng, int assign_thr, int center_thr,
-                                  float* center_t, float* bbox_t, long long* cls_t, int* box_idx, void* ws,
-                                  size_t ws_bytes, void* stream_) {
+// One launch pipeline for all B scans of the batch.
+//  points (Np,3) fp32, level by level (level_off: L+1 device ints); pt_batch (Np) scan of each point (NULL: one scan);
+//  boxes (NgT,9) gravity centre/size/euler and rneg (NgT,9) = R(-euler), labels (NgT) int64, concatenated over scans with
+//  box_off (B+1) device ints; max_ng = largest per-scan box count (host-known).
+//  Outputs: center_t (Np), bbox_t (Np,9), cls_t (Np) int64 (-1 = background), box_idx (Np) global box row or NULL.
+extern "C" int esb_fcaf3d_targets(const float* points, const int* level_off, int L, int Np, const int* pt_batch,
+                                  const float* boxes, const float* rneg, const long long* labels, const int* box_off,
+                                  int B, int NgT, int max_ng, int assign_thr, int center_thr, float* center_t,
+                                  float* bbox_t, long long* cls_t, int* box_idx, void* ws, size_t ws_bytes,
+                                  void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  ESB_CHECK_ARG(L >= 1 && Np >= 0 && Ng >= 1, "esb_fcaf3d_targets: need L>=1, Ng>=1 (the host handles Ng==0)");
-  if (ws_bytes < esb_fcaf3d_targets_workspace_bytes(L, Ng)) {
+  ESB_CHECK_ARG(L >= 1 && Np >= 0 && B >= 1 && NgT >= 0, "esb_fcaf3d_targets: bad sizes");
+  if (ws_bytes < esb_fcaf3d_targets_workspace_bytes(L, NgT, B)) {
     esb_set_error("esb_fcaf3d_targets: workspace too small");
     return ESB_ENOMEM;
   }
   if (Np == 0) return ESB_OK;
   char* p = (char*)ws;
-  int* counts = (int*)p; p += esb_align((size_t)L * Ng * 4);
-  int* best = (int*)p;   p += esb_align((size_t)Ng * 4);
-  float* top = (float*)p;
-  ESB_CUDA_CALL(cudaMemsetAsync(counts, 0, (size_t)L * Ng * 4, stream));
-  dim3 g1(esb_div_up(Np, 256), Ng);
-  count_inside_kernel<<<g1, 256, 0, stream>>>(points, level_off, L, Np, boxes, rneg, Ng, counts);
-  best_level_kernel<<<esb_div_up(Ng, 128), 128, 0, stream>>>(counts, L, Ng, assign_thr, best);
-  topk_threshold_kernel<<<Ng, 256, 0, stream>>>(points, level_off, Np, boxes, rneg, best, center_thr + 1, top);
-  assign_kernel<<<esb_div_up(Np, 128), 128, 0, stream>>>(points, level_off, L, Np, boxes, rneg, labels, Ng, best, top,
-                                                          center_t, bbox_t, cls_t, box_idx);
+  int* counts = (int*)p;      p += esb_align((size_t)L * NgT * 4);
+  int* best = (int*)p;        p += esb_align((size_t)NgT * 4);
+  float* top = (float*)p;     p += esb_align((size_t)NgT * 4);
+  int* n_pts_of_scan = (int*)p;
+  if (NgT > 0) {
+    ESB_CUDA_CALL(cudaMemsetAsync(counts, 0, (size_t)L * NgT * 4, stream));
+    ESB_CUDA_CALL(cudaMemsetAsync(n_pts_of_scan, 0, (size_t)B * 4, stream));
+    dim3 g1(esb_div_up(Np, 256), max_ng > 0 ? max_ng : 1);
+    count_inside_kernel<<<g1, 256, 0, stream>>>(points, level_off, L, Np, pt_batch, boxes, rneg, box_off, NgT, counts);
+    count_scan_points_kernel<<<esb_div_up(Np, 256), 256, 0, stream>>>(pt_batch, Np, n_pts_of_scan);
+    best_level_kernel<<<esb_div_up(NgT, 128), 128, 0, stream>>>(counts, L, NgT, assign_thr, best);
+    topk_threshold_kernel<<<NgT, 256, 0, stream>>>(points, level_off, pt_batch, n_pts_of_scan, boxes, rneg, box_off, B,
+                                                    best, center_thr + 1, top);
+  }
+  assign_kernel<<<esb_div_up(Np, 128), 128, 0, stream>>>(points, level_off, L, Np, pt_batch, boxes, rneg, labels, box_off,
+                                                          best, top, center_t, bbox_t, cls_t, box_idx);
   ESB_CUDA_LAUNCH_CHECK("esb_fcaf3d_targets");
   return ESB_OK;
 }
 
 // loss_sum: device fp32 scalar, accumulated (caller zeroes). logits (n,C) row-major.
+// row_w: optional (n) per-row weight (e.g. 1 / n_pos of the row's scan)
 extern "C" int esb_focal_loss_fwd(const void* logits, const long long* target, long long n, int C, float gamma,
-                                  float alpha, float* loss_sum, int dtype, void* stream) {
+                                  float alpha, const float* row_w, float* loss_sum, int dtype, void* stream) {
   if (n == 0) return ESB_OK;
   int grid = esb_div_up(n * C, 256);
   if (dtype == ESB_F32)
-    focal_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)logits, target, n, C, gamma, alpha, loss_sum);
+    focal_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)logits, target, n, C, gamma, alpha, row_w, loss_sum);
   else
     focal_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, n, C, gamma,
-                                                                             alpha, loss_sum);
+                                                                             alpha, row_w, loss_sum);
   ESB_CUDA_LAUNCH_CHECK("focal_fwd_kernel");
   return ESB_OK;
 }
 
 extern "C" int esb_focal_loss_bwd(const void* logits, const long long* target, long long n, int C, float gamma,
-                                  float alpha, const float* scale_dev, void* grad, int dtype, void* stream) {
+                                  float alpha, const float* row_w, const float* scale_dev, void* grad, int dtype,
+                                  void* stream) {
   if (n == 0) return ESB_OK;
   int grid = esb_div_up(n * C, 256);
   if (dtype == ESB_F32)
     focal_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)logits, target, n, C, gamma, alpha,
-                                                                     scale_dev, (float*)grad);
+                                                                     row_w, scale_dev, (float*)grad);
   else
     focal_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, n, C, gamma,
-                                                                             alpha, scale_dev, (__nv_bfloat16*)grad);
+                                                                             alpha, row_w, scale_dev, (__nv_bfloat16*)grad);
   ESB_CUDA_LAUNCH_CHECK("focal_bwd_kernel");
   return ESB_OK;
 }

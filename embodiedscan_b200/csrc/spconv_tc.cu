@@ -128,7 +128,9 @@ __global__ void tile_mask_kernel(const int* __restrict__ nbr, int K, int n, uint
 // ------------------------------------------------------------------------------------------------------------
 // forward / dgrad
 // ------------------------------------------------------------------------------------------------------------
-template <int N_TILE, int STAGES>
+// B_MN = false: wt is (K, cout, cin)  (W_k^T, reduction dim contiguous  -> K-major B; used by dgrad with wt = W itself)
+// B_MN = true : wt is (K, cin, cout)  (W_k as stored, output dim contiguous -> MN-major B; used by forward, no transpose)
+template <int N_TILE, int STAGES, bool B_MN>
 __global__ void __launch_bounds__(160)
 spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wt,
                      const int* __restrict__ nbr, const uint32_t* __restrict__ masks, __nv_bfloat16* __restrict__ y,
@@ -176,7 +178,7 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
       const int src = row < n_out ? nbr[(long long)k * n_out + row] : -1;
       const __nv_bfloat16* xrow = x + (long long)(src >= 0 ? src : 0) * cin;
       const int nbytes = src >= 0 ? 16 : 0;
-      const __nv_bfloat16* wk = wt + ((long long)k * cout + n0) * cin;
+      const __nv_bfloat16* wk = B_MN ? wt + (long long)k * cin * cout + n0 : wt + ((long long)k * cout + n0) * cin;
       for (int c = 0; c < nchunk; ++c, ++it) {
         const int s = it % STAGES;
         if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
@@ -187,9 +189,15 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 #pragma unroll
         for (int q = 0; q < N_TILE / 16; ++q) {
           const int idx = q * 128 + r;
-          const int n = idx >> 3, j = idx & 7;
-          cp_async16_cg(b_base + (n >> 3) * 1024 + (n & 7) * 128 + ((j ^ (n & 7)) << 4),
-                        wk + (long long)n * cin + c * TC_BK + j * 8, 16);
+          if (B_MN) {   // 64 reduction rows (cin) x N_TILE/8 chunks along cout; canonical MN-major SW128 atoms
+            const int kk = idx / (N_TILE / 8), nc = idx % (N_TILE / 8);
+            cp_async16_cg(b_base + (nc >> 3) * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + (((nc & 7) ^ (kk & 7)) << 4),
+                          wk + (long long)(c * TC_BK + kk) * cout + nc * 8, 16);
+          } else {
+            const int n = idx >> 3, j = idx & 7;
+            cp_async16_cg(b_base + (n >> 3) * 1024 + (n & 7) * 128 + ((j ^ (n & 7)) << 4),
+                          wk + (long long)n * cin + c * TC_BK + j * 8, 16);
+          }
         }
         cp_async_commit();
         if (it >= LAG) {
@@ -234,7 +242,7 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     tc_fence_before();
   } else {
     // ---------------- MMA issuer (warp 4) ----------------
-    const uint32_t idesc = make_idesc(TC_M, N_TILE, 0, 0);
+    const uint32_t idesc = make_idesc(TC_M, N_TILE, 0, B_MN ? 1 : 0);
     for (int it = 0; it < total; ++it) {
       const int s = it % STAGES;
       mbar_wait(&full_bar[s], (it / STAGES) & 1);
@@ -245,7 +253,7 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 #pragma unroll
         for (int kk = 0; kk < TC_BK / 16; ++kk) {
           uint64_t ad = make_desc(a_addr + kk * 32, 16, 1024);
-          uint64_t bd = make_desc(b_addr + kk * 32, 16, 1024);
+          uint64_t bd = B_MN ? make_desc(b_addr + kk * 2048, 8192, 1024) : make_desc(b_addr + kk * 32, 16, 1024);
           umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
@@ -394,11 +402,11 @@ spconv_tc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   (void)NB_ATOMS;
 }
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, bool B_MN>
 int launch_fwd(const void* x, const void* wt, const int* nbr, const unsigned* masks, void* y, long long n_out, int cin,
                int cout, int K, cudaStream_t stream) {
   size_t smem = (size_t)STAGES * (A_STAGE_BYTES + N_TILE * 128) + 1024 + 256;
-  auto kern = spconv_tc_fwd_kernel<N_TILE, STAGES>;
+  auto kern = spconv_tc_fwd_kernel<N_TILE, STAGES, B_MN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { esb_set_error("spconv_tc_fwd: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
   dim3 grid(esb_div_up(n_out, TC_M), cout / N_TILE);
@@ -431,10 +439,12 @@ extern "C" int esb_kmap_tile_masks(const int* nbr, int K, long long n, unsigned*
   return ESB_OK;
 }
 
-// bf16 tensor-core forward / dgrad. x (n_in,cin) ; wt (K,cout,cin) [W_k^T, reduction dim contiguous] ; nbr (K,n_out);
-// masks from esb_kmap_tile_masks(nbr) ; y (n_out,cout). Requires cin % 64 == 0 and cout % 64 == 0.
+// bf16 tensor-core forward / dgrad. x (n_in,cin) ; nbr (K,n_out) ; masks from esb_kmap_tile_masks(nbr) ; y (n_out,cout).
+// w_layout 0: w is (K,cout,cin) (reduction dim contiguous) ; w_layout 1: w is (K,cin,cout) (output dim contiguous).
+// Forward passes the stored kernel with w_layout 1; dgrad passes the same tensor with roles swapped and w_layout 0.
+// Requires cin % 64 == 0 and cout % 64 == 0.
 extern "C" int esb_spconv_tc_fwd(const void* x, const void* wt, const int* nbr, const unsigned* masks, void* y,
-                                 long long n_out, int cin, int cout, int K, void* stream_) {
+                                 long long n_out, int cin, int cout, int K, int w_layout, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ESB_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0 && cin > 0 && cout > 0, "esb_spconv_tc_fwd: channels must be multiples of 64");
   ESB_CHECK_ARG(K >= 1 && K <= 27, "esb_spconv_tc_fwd: K must be in [1,27]");
@@ -442,12 +452,16 @@ extern "C" int esb_spconv_tc_fwd(const void* x, const void* wt, const int* nbr, 
   int rc;
   // wide tiles amortise the gather; narrow tiles when there are too few row tiles to fill 148 SMs
   long long row_tiles = (n_out + TC_M - 1) / TC_M;
+#define ESB_TC_LAUNCH(NT, ST)                                                                         \
+  (w_layout ? launch_fwd<NT, ST, true>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream)             \
+            : launch_fwd<NT, ST, false>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream))
   if (cout % 256 == 0 && row_tiles * (cout / 256) >= 148)
-    rc = launch_fwd<256, 4>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream);
+    rc = ESB_TC_LAUNCH(256, 4);
   else if (cout % 128 == 0 && row_tiles * (cout / 128) >= 148)
-    rc = launch_fwd<128, 3>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream);
+    rc = ESB_TC_LAUNCH(128, 3);
   else
-    rc = launch_fwd<64, 4>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream);
+    rc = ESB_TC_LAUNCH(64, 4);
+#undef ESB_TC_LAUNCH
   if (rc != ESB_OK) return rc;
   ESB_CUDA_LAUNCH_CHECK("spconv_tc_fwd_kernel");
   return ESB_OK;

@@ -41,16 +41,22 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const int* __restri
   if (i >= 0) dx[(long long)i * C + c] = dy[t];
 }
 
+// seg_off == NULL means ONE segment covering all n_total rows (BatchNorm): no host->device offset upload per call
+__device__ __forceinline__ int seg_begin(const int* __restrict__ seg_off, int s) { return seg_off ? seg_off[s] : 0; }
+__device__ __forceinline__ int seg_end(const int* __restrict__ seg_off, int s, int n_total) {
+  return seg_off ? seg_off[s + 1] : n_total;
+}
+
 // ---------------- segmented column statistics ----------------
 // pass 1: sum over rows of each segment -> out[s][c]; pass 2 (centered): sum (x-mean)^2.
 template <typename T, int MODE>  // MODE 0: sum x ; 1: sum (x - mean[s][c])^2
 __global__ void seg_colstat_kernel(const T* __restrict__ x, const int* __restrict__ seg_off, const float* __restrict__ mean,
-                                   float* __restrict__ out, int C, int rows_per_block) {
+                                   float* __restrict__ out, int C, int rows_per_block, int n_total) {
   __shared__ float red[8][33];
   const int s = blockIdx.y;
   const int c = blockIdx.z * 32 + threadIdx.x;
-  const int r_beg = seg_off[s] + blockIdx.x * rows_per_block;
-  const int r_end = min(seg_off[s + 1], r_beg + rows_per_block);
+  const int r_beg = seg_begin(seg_off, s) + blockIdx.x * rows_per_block;
+  const int r_end = min(seg_end(seg_off, s, n_total), r_beg + rows_per_block);
   float acc = 0.f;
   if (c < C) {
     float mu = MODE == 1 ? mean[s * C + c] : 0.f;
@@ -75,22 +81,23 @@ __global__ void seg_colstat_kernel(const T* __restrict__ x, const int* __restric
 }
 
 // mean = sum / n ; (in place)
-__global__ void seg_finalize_mean_kernel(float* __restrict__ sum, const int* __restrict__ seg_off, int S, int C) {
+__global__ void seg_finalize_mean_kernel(float* __restrict__ sum, const int* __restrict__ seg_off, int S, int C,
+                                         int n_total) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= S * C) return;
   int s = t / C;
-  int n = seg_off[s + 1] - seg_off[s];
+  int n = seg_end(seg_off, s, n_total) - seg_begin(seg_off, s);
   sum[t] = n > 0 ? sum[t] / (float)n : 0.f;
 }
 // var(biased) -> rstd ; optionally update running stats (momentum, unbiased var) like nn.BatchNorm1d
 __global__ void seg_finalize_rstd_kernel(const float* __restrict__ mean, float* __restrict__ var_to_rstd,
                                          const int* __restrict__ seg_off, int S, int C, float eps,
                                          float* __restrict__ running_mean, float* __restrict__ running_var,
-                                         float momentum) {
+                                         float momentum, int n_total) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= S * C) return;
   int s = t / C;
-  int n = seg_off[s + 1] - seg_off[s];
+  int n = seg_end(seg_off, s, n_total) - seg_begin(seg_off, s);
   float var = n > 0 ? var_to_rstd[t] / (float)n : 0.f;
   if (running_mean != nullptr && S == 1) {
     float unbiased = n > 1 ? var * (float)n / (float)(n - 1) : var;
@@ -134,13 +141,13 @@ template <typename T>
 __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
                                        const int* __restrict__ seg_off, const float* __restrict__ mean,
                                        const float* __restrict__ rstd, float* __restrict__ sg, float* __restrict__ sgx,
-                                       int C, int rows_per_block, int act) {
+                                       int C, int rows_per_block, int act, int n_total) {
   __shared__ float red0[8][33];
   __shared__ float red1[8][33];
   const int s = blockIdx.y;
   const int c = blockIdx.z * 32 + threadIdx.x;
-  const int r_beg = seg_off[s] + blockIdx.x * rows_per_block;
-  const int r_end = min(seg_off[s + 1], r_beg + rows_per_block);
+  const int r_beg = seg_begin(seg_off, s) + blockIdx.x * rows_per_block;
+  const int r_end = min(seg_end(seg_off, s, n_total), r_beg + rows_per_block);
   float a0 = 0.f, a1 = 0.f;
   if (c < C) {
     float mu = mean[s * C + c], rs = rstd[s * C + c];
@@ -180,7 +187,7 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restri
   long long r = t / C;
   int c = (int)(t - r * C);
   int s = row_seg ? row_seg[r] : 0;
-  float inv_n = 1.f / (float)max(seg_off[s + 1] - seg_off[s], 1);
+  float inv_n = 1.f / (float)max(seg_end(seg_off, s, (int)N) - seg_begin(seg_off, s), 1);
   float g = esb_to_float<T>(dy[t]) * act_bwd_from_out(esb_to_float<T>(y[t]), act);
   float rs = rstd[s * C + c];
   float xh = (esb_to_float<T>(x[t]) - mean[s * C + c]) * rs;
@@ -231,12 +238,14 @@ extern "C" int esb_maxpool_bwd(const void* dy, const int* arg, void* dx, long lo
 //  seg_off (S+1) device int32 row offsets (rows of a segment are contiguous); row_seg (N) segment id per row or NULL
 //  when S==1. mean/rstd (S,C) fp32 outputs (saved for backward). gamma/beta may be NULL. res may be NULL.
 //  running_mean/var (C) updated when non-NULL and S==1 (BatchNorm training semantics, unbiased running var).
+// seg_off may be NULL when S == 1 (one segment = all N rows).
 extern "C" int esb_norm_fwd(const void* x, const void* res, const int* seg_off, const int* row_seg, int S,
                             long long N, int max_seg_rows, int C, const float* gamma, const float* beta, float eps,
                             float* running_mean, float* running_var, float momentum, int act, float* mean, float* rstd,
                             void* y, int dtype, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ESB_CHECK_ARG(S >= 1 && C >= 1, "esb_norm_fwd: bad S/C");
+  ESB_CHECK_ARG(seg_off != nullptr || S == 1, "esb_norm_fwd: seg_off may be NULL only for a single segment");
   ESB_CUDA_CALL(cudaMemsetAsync(mean, 0, sizeof(float) * S * C, stream));
   ESB_CUDA_CALL(cudaMemsetAsync(rstd, 0, sizeof(float) * S * C, stream));
   if (N == 0) return ESB_OK;
@@ -244,10 +253,11 @@ extern "C" int esb_norm_fwd(const void* x, const void* res, const int* seg_off, 
   dim3 grid(esb_div_up(max_seg_rows > 0 ? max_seg_rows : 1, rpb), S, esb_div_up(C, 32)), block(32, 8);
   int fin = esb_div_up(S * C, 256);
   DISPATCH_T(dtype, {
-    seg_colstat_kernel<T, 0><<<grid, block, 0, stream>>>((const T*)x, seg_off, nullptr, mean, C, rpb);
-    seg_finalize_mean_kernel<<<fin, 256, 0, stream>>>(mean, seg_off, S, C);
-    seg_colstat_kernel<T, 1><<<grid, block, 0, stream>>>((const T*)x, seg_off, mean, rstd, C, rpb);
-    seg_finalize_rstd_kernel<<<fin, 256, 0, stream>>>(mean, rstd, seg_off, S, C, eps, running_mean, running_var, momentum);
+    seg_colstat_kernel<T, 0><<<grid, block, 0, stream>>>((const T*)x, seg_off, nullptr, mean, C, rpb, (int)N);
+    seg_finalize_mean_kernel<<<fin, 256, 0, stream>>>(mean, seg_off, S, C, (int)N);
+    seg_colstat_kernel<T, 1><<<grid, block, 0, stream>>>((const T*)x, seg_off, mean, rstd, C, rpb, (int)N);
+    seg_finalize_rstd_kernel<<<fin, 256, 0, stream>>>(mean, rstd, seg_off, S, C, eps, running_mean, running_var, momentum,
+                                                      (int)N);
     norm_apply_kernel<T><<<esb_div_up(N * C, 256), 256, 0, stream>>>((const T*)x, (const T*)res, row_seg, mean, rstd,
                                                                      gamma, beta, (T*)y, N, C, act);
   });
@@ -279,7 +289,7 @@ extern "C" int esb_norm_bwd(const void* x, const void* y, const void* dy, const 
   dim3 grid(esb_div_up(max_seg_rows > 0 ? max_seg_rows : 1, rpb), S, esb_div_up(C, 32)), block(32, 8);
   DISPATCH_T(dtype, {
     norm_bwd_reduce_kernel<T><<<grid, block, 0, stream>>>((const T*)x, (const T*)y, (const T*)dy, seg_off, mean, rstd,
-                                                          sg, sgx, C, rpb, act);
+                                                          sg, sgx, C, rpb, act, (int)N);
     norm_bwd_apply_kernel<T><<<esb_div_up(N * C, 256), 256, 0, stream>>>(
         (const T*)x, (const T*)y, (const T*)dy, row_seg, seg_off, mean, rstd, gamma, sg, sgx, (T*)dx, (T*)dres, N, C, act);
   });

@@ -15,8 +15,8 @@ import torch.nn.functional as F
 from . import _ffi
 from . import sparse as SP
 from ._ffi import call, ptr, query, stream
-from .geometry import (bbox_cd_loss, euler_angles_to_matrix, matrix_to_euler_angles_zxy, ortho_6d_2_mat,
-                       rotation_3d_in_euler)
+from .geometry import (bbox_cd_loss, bbox_to_corners, chamfer_l1_src, euler_angles_to_matrix,
+                       matrix_to_euler_angles_zxy, ortho_6d_2_mat, rotation_3d_in_euler)
 from .registry import MODELS
 from .structures import EulerDepthInstance3DBoxes, InstanceData
 
@@ -55,32 +55,35 @@ class FocalLoss(nn.Module):
         assert use_sigmoid and reduction == 'mean'
         self.gamma, self.alpha, self.loss_weight = gamma, alpha, loss_weight
 
-    def forward(self, pred, target, avg_factor):
-        return _Focal.apply(pred, target, avg_factor, self.gamma, self.alpha) * self.loss_weight
+    def forward(self, pred, target, avg_factor=None, row_weight=None):
+        """sum(focal) / avg_factor, or sum(row_weight[r] * focal[r, :]) when per-row weights are given."""
+        if row_weight is None:
+            row_weight = (1.0 / avg_factor.to(torch.float32).reshape(1)).expand(pred.shape[0]).contiguous()
+        return _Focal.apply(pred, target, row_weight, self.gamma, self.alpha) * self.loss_weight
 
 
 class _Focal(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, logits, target, avg_factor, gamma, alpha):
+    def forward(ctx, logits, target, row_w, gamma, alpha):
         logits = logits.contiguous()
+        row_w = row_w.to(torch.float32).contiguous()
         n, C = logits.shape
         total = torch.zeros(1, dtype=torch.float32, device=logits.device)
-        call('esb_focal_loss_fwd', ptr(logits), ptr(target), n, C, gamma, alpha, ptr(total), _ffi.dtype_code(logits.dtype),
-             stream())
-        avg = avg_factor.to(torch.float32).reshape(1)
-        ctx.save_for_backward(logits, target, avg)
+        call('esb_focal_loss_fwd', ptr(logits), ptr(target), n, C, gamma, alpha, ptr(row_w), ptr(total),
+             _ffi.dtype_code(logits.dtype), stream())
+        ctx.save_for_backward(logits, target, row_w)
         ctx.hp = (gamma, alpha)
-        return (total / avg).squeeze(0)
+        return total.squeeze(0)
 
     @staticmethod
     def backward(ctx, g):
-        logits, target, avg = ctx.saved_tensors
+        logits, target, row_w = ctx.saved_tensors
         gamma, alpha = ctx.hp
-        scale = (g.to(torch.float32).reshape(1) / avg).contiguous()
+        scale = g.to(torch.float32).reshape(1).contiguous()
         grad = torch.empty_like(logits)
         n, C = logits.shape
-        call('esb_focal_loss_bwd', ptr(logits), ptr(target), n, C, gamma, alpha, ptr(scale), ptr(grad),
+        call('esb_focal_loss_bwd', ptr(logits), ptr(target), n, C, gamma, alpha, ptr(row_w), ptr(scale), ptr(grad),
              _ffi.dtype_code(logits.dtype), stream())
         return grad, None, None, None, None
 
@@ -99,31 +102,45 @@ class CrossEntropyLoss(nn.Module):
         return loss.sum() / avg_factor * self.loss_weight
 
 
-def fcaf3d_targets(points_lvls: List[torch.Tensor], gt_boxes9: torch.Tensor, gt_labels: torch.Tensor,
-                   assign_thr: int, center_thr: int):
-    """Fused get_targets (fcaf3d_head.py:1578-1664). points per level (n_l, 3); boxes (Ng, 9) gravity-centred."""
-    dev = points_lvls[0].device
-    pts = torch.cat(points_lvls).float().contiguous()
-    Np, L = pts.shape[0], len(points_lvls)
-    Ng = gt_boxes9.shape[0]
-    if Ng == 0:
-        return (pts.new_zeros((Np, )), pts.new_zeros((Np, gt_boxes9.shape[-1])),
-                gt_labels.new_full((Np, ), -1))
+def fcaf3d_targets_batched(points: torch.Tensor, level_sizes: List[int], pt_batch: Optional[torch.Tensor],
+                            boxes9_list: List[torch.Tensor], labels_list: List[torch.Tensor], assign_thr: int,
+                            center_thr: int):
+    """Fused get_targets (fcaf3d_head.py:1578-1664) for ALL scans of the batch in one kernel pipeline.
+    points (Np,3) level by level (natural row order, scans interleaved), pt_batch (Np) int32 scan ids,
+    boxes9_list[b] (Ng_b, 9) gravity-centred. Returns center_t (Np), bbox_t (Np,9), cls_t (Np) int64."""
+    dev = points.device
+    pts = points.float().contiguous()
+    Np, L, B = pts.shape[0], len(level_sizes), len(boxes9_list)
     offs = [0]
-    for p in points_lvls:
-        offs.append(offs[-1] + p.shape[0])
-    level_off = torch.tensor(offs, dtype=torch.int32, device=dev)
-    boxes = gt_boxes9.float().contiguous()
-    rneg = euler_angles_to_matrix(-boxes[:, 6:9], 'ZXY').contiguous().view(Ng, 9)
-    labels = gt_labels.to(torch.int64).contiguous()
+    for n in level_sizes:
+        offs.append(offs[-1] + n)
+    box_offs = [0]
+    for bx in boxes9_list:
+        box_offs.append(box_offs[-1] + bx.shape[0])
+    NgT, max_ng = box_offs[-1], max([bx.shape[0] for bx in boxes9_list] + [0])
+    meta = torch.tensor(offs + box_offs, dtype=torch.int32).to(dev, non_blocking=True)
+    level_off, box_off = meta[:L + 1], meta[L + 1:]
+    boxes = torch.cat([bx.float() for bx in boxes9_list]).to(dev).contiguous() if NgT else pts.new_zeros((0, 9))
+    labels = torch.cat([lb.to(torch.int64) for lb in labels_list]).to(dev).contiguous() if NgT else \
+        torch.zeros((0, ), dtype=torch.int64, device=dev)
+    rneg = euler_angles_to_matrix(-boxes[:, 6:9], 'ZXY').contiguous().view(-1, 9)
     center_t = torch.empty(Np, dtype=torch.float32, device=dev)
     bbox_t = torch.empty((Np, 9), dtype=torch.float32, device=dev)
     cls_t = torch.empty(Np, dtype=torch.int64, device=dev)
-    wsb = query('esb_fcaf3d_targets_workspace_bytes', L, Ng)
+    wsb = query('esb_fcaf3d_targets_workspace_bytes', L, max(NgT, 1), B)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    call('esb_fcaf3d_targets', ptr(pts), ptr(level_off), L, Np, ptr(boxes), ptr(rneg), ptr(labels), Ng, assign_thr,
-         center_thr, ptr(center_t), ptr(bbox_t), ptr(cls_t), None, ptr(ws), wsb, stream())
+    call('esb_fcaf3d_targets', ptr(pts), ptr(level_off), L, Np, ptr(pt_batch), ptr(boxes), ptr(rneg), ptr(labels),
+         ptr(box_off), B, NgT, max_ng, assign_thr, center_thr, ptr(center_t), ptr(bbox_t), ptr(cls_t), None, ptr(ws), wsb,
+         stream())
     return center_t, bbox_t, cls_t
+
+
+def fcaf3d_targets(points_lvls: List[torch.Tensor], gt_boxes9: torch.Tensor, gt_labels: torch.Tensor,
+                   assign_thr: int, center_thr: int):
+    """Single-scan form of the reference's get_targets(points, gt_bboxes, gt_labels)."""
+    return fcaf3d_targets_batched(torch.cat(points_lvls), [p.shape[0] for p in points_lvls], None,
+                                  [gt_boxes9.to(points_lvls[0].device)], [gt_labels.to(points_lvls[0].device)],
+                                  assign_thr, center_thr)
 
 
 def multiclass_nms_bev(bboxes: torch.Tensor, scores: torch.Tensor, score_thr: float, iou_thr: float,
@@ -225,8 +242,10 @@ class FCAF3DHeadRotMat(nn.Module):
             x = SP.conv_norm_act(mods[i], mods[i + 1], SP.ACT_ELU, x, training=self.training)
         return x
 
-    def forward(self, x: List[SP.SparseTensor]):
-        center_preds, bbox_preds, cls_preds, points = [], [], [], []
+    def _forward_levels(self, x: List[SP.SparseTensor]):
+        """Top-down pass (fcaf3d_head.py:993-1020). Returns, per level (fine -> coarse), a dict of whole-batch tensors
+        center (N,1), bbox (N,12), cls (N,C), points (N,3), batch (N,) int32, perms (per-scan row indices)."""
+        outs = []
         inputs = x
         x = inputs[-1]
         prune_score = None
@@ -236,16 +255,26 @@ class FCAF3DHeadRotMat(nn.Module):
                 x = inputs[i] + x
                 x = self._prune(x, prune_score)
             out = self._run_block(getattr(self, f'out_block_{i}'), x)
-            center_pred, bbox_pred, cls_pred, point, prune_score = self._forward_single(out, self.scales[i])
-            center_preds.append(center_pred)
-            bbox_preds.append(bbox_pred)
-            cls_preds.append(cls_pred)
-            points.append(point)
-        return center_preds[::-1], bbox_preds[::-1], cls_preds[::-1], points[::-1]
+            lv, prune_score = self._forward_single_level(out, self.scales[i], need_prune_score=i > 0)
+            outs.append(lv)
+        return outs[::-1]
+
+    def forward(self, x: List[SP.SparseTensor]):
+        """Reference return format: four lists (level-major) of per-scan tensor lists."""
+        center_preds, bbox_preds, cls_preds, points = [], [], [], []
+        for lv in self._forward_levels(x):
+            perms = lv['tensor'].decomposition_permutations
+            center_preds.append([lv['center'][p] for p in perms])
+            bbox_preds.append([lv['bbox'][p] for p in perms])
+            cls_preds.append([lv['cls'][p] for p in perms])
+            points.append([lv['points'][p] for p in perms])
+        return center_preds, bbox_preds, cls_preds, points
 
     def _prune(self, x: SP.SparseTensor, scores: SP.SparseTensor) -> SP.SparseTensor:
         """Per-scan top-k by the multilinearly interpolated parent max-class score (fcaf3d_head.py:1091-1114).
-        Identity whenever every scan holds <= pts_prune_threshold rows (always the case for mv-det: 100000)."""
+        Identity whenever every scan holds <= pts_prune_threshold rows."""
+        if len(x) <= self.pts_prune_threshold:      # no scan can exceed the threshold: skip without a host sync
+            return x
         perms, _, counts = x.cmap.decomposition(x.coordinate_manager.batch_size)
         if max(counts) <= self.pts_prune_threshold:
             return x
@@ -260,32 +289,27 @@ class FCAF3DHeadRotMat(nn.Module):
                 prune_mask[perm[ids]] = True
         return self.pruning(x, prune_mask)
 
-    def _forward_single(self, x: SP.SparseTensor, scale: Scale):
+    def _forward_single_level(self, x: SP.SparseTensor, scale: Scale, need_prune_score: bool = True):
+        """_forward_single (fcaf3d_head.py:1116-1149) on whole-batch rows; the three 1x1 heads are two GEMMs."""
         f = x.F
-        # the three 1x1 heads share one GEMM: (N,128) x (128, 1+12+284)
-        w = torch.cat([self.conv_center.kernel, self.conv_reg.kernel, self.conv_cls.kernel], 1).to(f.dtype)
-        heads = (f @ w).float()
-        nr = self.conv_reg.kernel.shape[1]
-        center_pred = heads[:, :1]
-        reg_final = heads[:, 1:1 + nr]
-        cls_pred = heads[:, 1 + nr:] + self.conv_cls.bias.float()
-        prune_scores = x.replace_feature(cls_pred.max(dim=1, keepdim=True).values)
+        w_small = torch.cat([self.conv_center.kernel, self.conv_reg.kernel], 1).to(f.dtype)
+        small = (f @ w_small).float()
+        center_pred = small[:, :1]
+        reg_final = small[:, 1:]
+        cls_pred = torch.addmm(self.conv_cls.bias.to(f.dtype), f, self.conv_cls.kernel.to(f.dtype))
+        prune_scores = x.replace_feature(cls_pred.max(dim=1, keepdim=True).values.float()) if need_prune_score else None
         reg_distance = torch.exp(scale(reg_final[:, :6])).clamp(min=1e-3)
         bbox_pred = torch.cat((reg_distance, reg_final[:, 6:]), dim=1)
-        center_preds, bbox_preds, cls_preds = [], [], []
-        for perm in x.decomposition_permutations:
-            center_preds.append(center_pred[perm])
-            bbox_preds.append(bbox_pred[perm])
-            cls_preds.append(cls_pred[perm])
-        points = [c * self.voxel_size for c in x.decomposed_coordinates]
-        return center_preds, bbox_preds, cls_preds, points, prune_scores
+        coords = x.C
+        lv = dict(center=center_pred, bbox=bbox_pred, cls=cls_pred, points=coords[:, 1:] * self.voxel_size,
+                  batch=coords[:, 0].contiguous(), tensor=x)
+        return lv, prune_scores
 
     # ---- loss ---------------------------------------------------------------------------------------------
     def loss(self, x, batch_data_samples, **kwargs) -> dict:
-        outs = self(x)
+        levels = self._forward_levels(x)
         gts = [ds.gt_instances_3d for ds in batch_data_samples]
-        metas = [ds.metainfo for ds in batch_data_samples]
-        return self.loss_by_feat(*outs, gts, metas)
+        return self.loss_by_levels(levels, gts)
 
     def _reduce_mean(self, t: torch.Tensor) -> torch.Tensor:
         """utils/dist_utils.py:4-10 for the whole batch at once, on the device."""
@@ -296,62 +320,76 @@ class FCAF3DHeadRotMat(nn.Module):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
         return t
 
-    def loss_by_feat(self, center_preds, bbox_preds, cls_preds, points, batch_gt_instances_3d, batch_input_metas,
+    def loss_by_feat(self, center_preds, bbox_preds, cls_preds, points, batch_gt_instances_3d, batch_input_metas=None,
                      batch_gt_instances_ignore=None, **kwargs) -> dict:
-        B = len(batch_input_metas)
-        per = []
-        for i in range(B):
-            pts_l = [p[i] for p in points]
-            gt = batch_gt_instances_3d[i]
-            boxes = gt.bboxes_3d
-            boxes9 = torch.cat((boxes.gravity_center, boxes.tensor[:, 3:]), 1).to(pts_l[0].device)
-            targets = fcaf3d_targets(pts_l, boxes9, gt.labels_3d.to(pts_l[0].device), self.pts_assign_threshold,
-                                     self.pts_center_threshold)
-            per.append(targets)
-        n_pos_local = torch.stack([(t[2] >= 0).sum().float() for t in per])
-        n_pos = torch.clamp(self._reduce_mean(n_pos_local), min=1.)
-        center_losses, bbox_losses, cls_losses = [], [], []
-        for i in range(B):
-            c, b, k = self._loss_by_feat_single([x[i] for x in center_preds], [x[i] for x in bbox_preds],
-                                                [x[i] for x in cls_preds], [x[i] for x in points], per[i], n_pos[i])
-            center_losses.append(c)
-            bbox_losses.append(b)
-            cls_losses.append(k)
-        return dict(loss_center=torch.mean(torch.stack(center_losses)),
-                    loss_bbox=torch.mean(torch.stack(bbox_losses)), loss_cls=torch.mean(torch.stack(cls_losses)))
+        """Reference signature (lists of per-scan tensors); regrouped into whole-batch rows for the fused path."""
+        dev = points[0][0].device
+        levels = []
+        for l in range(len(points)):
+            B = len(points[l])
+            levels.append(dict(center=torch.cat(center_preds[l]), bbox=torch.cat(bbox_preds[l]), cls=torch.cat(cls_preds[l]),
+                               points=torch.cat(points[l]),
+                               batch=torch.cat([torch.full((len(points[l][b]), ), b, dtype=torch.int32, device=dev)
+                                                for b in range(B)])))
+        return self.loss_by_levels(levels, batch_gt_instances_3d)
 
-    def _loss_by_feat_single(self, center_preds, bbox_preds, cls_preds, points, targets, n_pos):
-        center_targets, bbox_targets, cls_targets = targets
-        center_preds = torch.cat(center_preds)
-        bbox_preds = torch.cat(bbox_preds)
-        cls_preds = torch.cat(cls_preds)
-        points = torch.cat(points)
-        cls_loss = self.cls_loss(cls_preds, cls_targets, avg_factor=n_pos)
-        pos_inds = torch.nonzero(cls_targets >= 0).squeeze(1)
+    def loss_by_levels(self, levels, batch_gt_instances_3d) -> dict:
+        """_loss_by_feat_single (fcaf3d_head.py:1151-1294) + the batch mean (:1334-1350), evaluated for all scans at once:
+        per-scan normalisers become per-row weights, so there is no Python loop over scans and one host sync."""
+        B = len(batch_gt_instances_3d)
+        dev = levels[0]['points'].device
+        pts = torch.cat([lv['points'] for lv in levels])
+        pt_batch = torch.cat([lv['batch'] for lv in levels]).contiguous()
+        sizes = [lv['points'].shape[0] for lv in levels]
+        boxes9 = [torch.cat((g.bboxes_3d.gravity_center, g.bboxes_3d.tensor[:, 3:]), 1) for g in batch_gt_instances_3d]
+        labels = [g.labels_3d for g in batch_gt_instances_3d]
+        center_t, bbox_t, cls_t = fcaf3d_targets_batched(pts, sizes, pt_batch, boxes9, labels, self.pts_assign_threshold,
+                                                         self.pts_center_threshold)
+        pos_mask = cls_t >= 0
+        pb_all = pt_batch.long()
+        n_pos_local = torch.zeros(B, dtype=torch.float32, device=dev).index_add_(0, pb_all, pos_mask.float())
+        n_pos = torch.clamp(self._reduce_mean(n_pos_local.clone()), min=1.)          # (B,) one fused all-reduce
+        row_w = (1.0 / (n_pos * B))[pb_all]                                         # 1/(n_pos[scan] * B) per row
+        # classification: sum_rows focal(row) / n_pos[scan(row)], mean over scans
+        loss_cls, off = 0., 0
+        for lv, n in zip(levels, sizes):
+            loss_cls = loss_cls + self.cls_loss(lv['cls'], cls_t[off:off + n], row_weight=row_w[off:off + n])
+            off += n
+        center_preds = torch.cat([lv['center'] for lv in levels])
+        bbox_preds = torch.cat([lv['bbox'] for lv in levels])
+        pos_inds = torch.nonzero(pos_mask).squeeze(1)                                # the one host sync of the loss
         pos_center_preds = center_preds[pos_inds]
         pos_bbox_preds = bbox_preds[pos_inds]
-        if len(pos_inds) > 0:
-            pos_center_targets = center_targets[pos_inds].unsqueeze(1)
-            pos_bbox_targets = bbox_targets[pos_inds]
-            pos_points = points[pos_inds]
-            center_loss = self.center_loss(pos_center_preds, pos_center_targets, avg_factor=n_pos)
-            decoded = self._bbox_pred_to_bbox(pos_points, pos_bbox_preds)
+        if pos_inds.numel() > 0:
+            w_pos = row_w[pos_inds]
+            bce = F.binary_cross_entropy_with_logits(pos_center_preds.float(), center_t[pos_inds].unsqueeze(1),
+                                                     reduction='none')
+            loss_center = (bce.squeeze(1) * w_pos).sum() * self.center_loss.loss_weight
+            tgt = bbox_t[pos_inds]
+            decoded = self._bbox_pred_to_bbox(pts[pos_inds], pos_bbox_preds)
+            tgt_corners = bbox_to_corners(tgt)
+            # per-scan mean over (P_scan x 8) corners, then mean over scans -> weight 1 / (8 * P_scan * B) per corner
+            p_scan = n_pos_local[pb_all[pos_inds]]
+            w_box = (1.0 / (8.0 * p_scan * B))[:, None]
+
+            def cd(src):
+                return (chamfer_l1_src(bbox_to_corners(src), tgt_corners) * w_box).sum() * self.bbox_loss.loss_weight
+
             if self.decouple_bbox_loss:
-                tc, ts, te = pos_bbox_targets[:, :3], pos_bbox_targets[:, 3:6], pos_bbox_targets[:, 6:]
+                tc, ts, te = tgt[:, :3], tgt[:, 3:6], tgt[:, 6:]
                 pc, ps, pe = decoded[:, :3], decoded[:, 3:6], decoded[:, 6:]
                 assert self.decouple_groups in (3, 4) and not self.norm_decouple_loss
                 w = self.decouple_weights
-                bbox_loss = w[0] * self.bbox_loss(torch.cat((pc, ts, te), -1), pos_bbox_targets)
-                bbox_loss = bbox_loss + w[1] * self.bbox_loss(torch.cat((tc, ps, te), -1), pos_bbox_targets)
-                bbox_loss = bbox_loss + w[2] * self.bbox_loss(torch.cat((tc, ts, pe), -1), pos_bbox_targets)
+                loss_bbox = w[0] * cd(torch.cat((pc, ts, te), -1)) + w[1] * cd(torch.cat((tc, ps, te), -1)) + \
+                    w[2] * cd(torch.cat((tc, ts, pe), -1))
                 if self.decouple_groups == 4:
-                    bbox_loss = bbox_loss + w[3] * self.bbox_loss(decoded, pos_bbox_targets)
+                    loss_bbox = loss_bbox + w[3] * cd(decoded)
             else:
-                bbox_loss = self.bbox_loss(decoded, pos_bbox_targets)
+                loss_bbox = cd(decoded)
         else:
-            center_loss = pos_center_preds.sum()
-            bbox_loss = pos_bbox_preds.sum()
-        return center_loss, bbox_loss, cls_loss
+            loss_center = pos_center_preds.sum()
+            loss_bbox = pos_bbox_preds.sum()
+        return dict(loss_center=loss_center, loss_bbox=loss_bbox, loss_cls=loss_cls)
 
     @staticmethod
     def _bbox_pred_to_bbox(points: torch.Tensor, bbox_pred: torch.Tensor) -> torch.Tensor:

@@ -123,7 +123,7 @@ class SparseFeatureFusionSingleStage3DDetector(nn.Module):
     def extract_feat(self, batch_inputs_dict: Dict[str, torch.Tensor], batch_data_samples) -> List[SP.SparseTensor]:
         points = batch_inputs_dict['points']
         coordinates, features = self.voxelize(points)
-        x = SP.SparseTensor(coordinates=coordinates, features=features.to(self.compute_dtype))
+        x = SP.SparseTensor(coordinates=coordinates, features=features.to(self.compute_dtype), batch_size=len(points))
         x = self.backbone_3d(x)
         num_levels = len(x)
 

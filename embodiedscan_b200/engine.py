@@ -31,10 +31,15 @@ class FlatArena:
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.offsets = offs
+        self.bf16 = torch.zeros(n, dtype=torch.bfloat16, device=dev) if dev.type == 'cuda' else None
         for p, o in zip(params, offs):
             self.flat[o:o + p.numel()].copy_(p.data.reshape(-1).float())
             p.data = self.flat[o:o + p.numel()].view_as(p)
             p.grad = self.grad[o:o + p.numel()].view_as(p)
+            if self.bf16 is not None:
+                p._esb_bf16 = self.bf16[o:o + p.numel()].view_as(p)     # bf16 operand copy, refreshed once per step
+                p._esb_grad_direct = True                                # kernels may accumulate into p.grad in place
+        self.refresh_bf16()
         # buckets: contiguous [start, end) ranges of ~bucket_bytes
         self.buckets, self.bucket_of = [], []
         start, cur = 0, 0
@@ -48,6 +53,11 @@ class FlatArena:
         self.n_params_in_bucket = [0] * len(self.buckets)
         for b in self.bucket_of:
             self.n_params_in_bucket[b] += 1
+
+    def refresh_bf16(self):
+        """fp32 master arena -> bf16 compute copy: ONE launch for the whole model."""
+        if self.bf16 is not None:
+            call('esb_cast_f32_to_bf16', ptr(self.flat), ptr(self.bf16), self.numel, stream())
 
     def zero_grad(self):
         self.grad.zero_()
@@ -140,9 +150,11 @@ class OptimWrapper:
         loss.backward()
         self.reducer.finish()
         self.optimizer.step()
+        self.arena.refresh_bf16()
         self.arena.zero_grad()
 
 
 def broadcast_parameters(arena: FlatArena, src: int = 0, process_group=None):
     if dist.is_initialized() and dist.get_world_size(process_group) > 1:
         dist.broadcast(arena.flat, src=src, group=process_group)
+    arena.refresh_bf16()

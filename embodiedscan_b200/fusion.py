@@ -92,7 +92,12 @@ def pack_projections(img_metas: Sequence[dict], coord_type: str, device) -> torc
         intr = pm['intrinsic']
         if not isinstance(intr, (list, tuple)):
             intr = [intr] * len(pm['extrinsic'])
-        mats.append(np.stack([compose_projection(intr[v], pm['extrinsic'][v]) for v in range(len(pm['extrinsic']))]))
+        a = np.stack([np.asarray(i, dtype=np.float32).reshape(4, 4) for i in intr])
+        b = np.stack([np.asarray(e, dtype=np.float32).reshape(4, 4) for e in pm['extrinsic']])
+        acc = np.zeros((a.shape[0], 4, 4), dtype=np.float32)
+        for k in range(4):        # same order as compose_projection: acc = fl(acc + fl(a[i,k] * b[k,j])), k = 0..3
+            acc = (acc + (a[:, :, k:k + 1] * b[:, k:k + 1, :]).astype(np.float32)).astype(np.float32)
+        mats.append(acc)
     return torch.from_numpy(np.stack(mats)).to(device)
 
 

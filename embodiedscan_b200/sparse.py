@@ -172,12 +172,14 @@ class CoordinateManager:
             raise RuntimeError('esb_coord_unique: coordinate outside the packable range (|xyz| < 32768, batch < 65535)')
         return CoordinateMap(out[:c], stride, keys, vals), in2out[:n]
 
-    def insert(self, coords: torch.Tensor, stride: int = 1):
+    def insert(self, coords: torch.Tensor, stride: int = 1, batch_size: Optional[int] = None):
         """Deduplicate raw coordinates. Returns (key, in2out)."""
         cmap, in2out = self._unique(coords.contiguous(), 1, stride)
         key = self.new_key(stride, 'input')
         self.maps[key] = cmap
-        self.batch_size = int(coords[:, 0].max().item()) + 1 if coords.shape[0] else 1
+        if batch_size is None:
+            batch_size = int(coords[:, 0].max().item()) + 1 if coords.shape[0] else 1
+        self.batch_size = batch_size
         return key, in2out
 
     def insert_unique(self, coords: torch.Tensor, stride: int):
@@ -253,18 +255,19 @@ class _SparseConv(torch.autograd.Function):
     def forward(ctx, x, weight, kmap: KernelMap, cin, cout):
         K = kmap.K
         x = x.contiguous()
-        w = weight.detach().to(x.dtype).contiguous()
+        w = getattr(weight, '_esb_bf16', None) if x.dtype == torch.bfloat16 else None   # arena shadow copy (engine.py)
+        if w is None:
+            w = weight.detach().to(x.dtype).contiguous()
         y = torch.empty((kmap.n_out, cout), dtype=x.dtype, device=x.device)
         tc = USE_TENSOR_CORES and x.dtype == torch.bfloat16 and cin % 64 == 0 and cout % 64 == 0
-        if tc:
-            wt = w.view(K, cin, cout).transpose(1, 2).contiguous()          # W_k^T: reduction dim contiguous
-            _timed_conv_call('fwd', kmap, cin, cout, x.dtype, 'esb_spconv_tc_fwd', ptr(x), ptr(wt), ptr(kmap.nbr_out),
-                             ptr(kmap.tile_masks('out')), ptr(y), kmap.n_out, cin, cout, K, stream())
+        if tc:   # the stored (K,cin,cout) kernel is the MN-major B operand: no transpose copy
+            _timed_conv_call('fwd', kmap, cin, cout, x.dtype, 'esb_spconv_tc_fwd', ptr(x), ptr(w), ptr(kmap.nbr_out),
+                             ptr(kmap.tile_masks('out')), ptr(y), kmap.n_out, cin, cout, K, 1, stream())
         else:
             _timed_conv_call('fwd', kmap, cin, cout, x.dtype, 'esb_spconv_fwd', ptr(x), ptr(w), ptr(kmap.nbr_out),
                              ptr(y), kmap.n_out, cin, cout, K, 0, 0, _ffi.dtype_code(x.dtype), stream())
         ctx.save_for_backward(x, w)
-        ctx.kmap, ctx.cin, ctx.cout, ctx.wshape, ctx.tc = kmap, cin, cout, weight.shape, tc
+        ctx.kmap, ctx.cin, ctx.cout, ctx.wshape, ctx.tc, ctx.weight = kmap, cin, cout, weight.shape, tc, weight
         return y
 
     @staticmethod
@@ -279,20 +282,28 @@ class _SparseConv(torch.autograd.Function):
             # dgrad = the forward kernel on the input-stationary map with W read transposed
             if ctx.tc:   # (K,cin,cout) already is the K-major B operand of the transposed problem
                 _timed_conv_call('dgrad', kmap, cout, cin, x.dtype, 'esb_spconv_tc_fwd', ptr(dy), ptr(w), ptr(kmap.nbr_in),
-                                 ptr(kmap.tile_masks('in')), ptr(dx), kmap.n_in, cout, cin, kmap.K, stream())
+                                 ptr(kmap.tile_masks('in')), ptr(dx), kmap.n_in, cout, cin, kmap.K, 0, stream())
             else:
                 _timed_conv_call('dgrad', kmap, cout, cin, x.dtype, 'esb_spconv_fwd', ptr(dy), ptr(w), ptr(kmap.nbr_in),
                                  ptr(dx), kmap.n_in, cout, cin, kmap.K, 1, 0, code, stream())
         if ctx.needs_input_grad[1]:
             pin, pout, koff, tot = kmap.pairs
-            dw = torch.zeros((kmap.K, cin, cout), dtype=torch.float32, device=x.device)
+            weight = ctx.weight
+            direct = getattr(weight, '_esb_grad_direct', False) and weight.grad is not None
+            # arena parameters: the kernel accumulates straight into the flat gradient buffer (no zeros + add_ pass)
+            dw = weight.grad if direct else torch.zeros((kmap.K, cin, cout), dtype=torch.float32, device=x.device)
             if ctx.tc and USE_TC_WGRAD:
                 _timed_conv_call('wgrad', kmap, cin, cout, x.dtype, 'esb_spconv_tc_wgrad', ptr(x), ptr(dy), ptr(pin),
                                  ptr(pout), ptr(koff), ptr(dw), tot, cin, cout, kmap.K, stream())
             else:
                 _timed_conv_call('wgrad', kmap, cin, cout, x.dtype, 'esb_spconv_wgrad', ptr(x), ptr(dy), ptr(pin),
                                  ptr(pout), ptr(koff), ptr(dw), tot, cin, cout, kmap.K, code, stream())
-            dw = dw.view(ctx.wshape)
+            if direct:
+                for hook in (getattr(weight, '_post_accumulate_grad_hooks', None) or {}).values():
+                    hook(weight)       # what autograd's AccumulateGrad would have fired (bucket all-reduce bookkeeping)
+                dw = None
+            else:
+                dw = dw.view(ctx.wshape)
         return dx, dw, None, None, None
 
 
@@ -336,7 +347,7 @@ class _SegNorm(torch.autograd.Function):
         call('esb_norm_fwd', ptr(x), ptr(resc), ptr(seg_off), ptr(row_seg), S, N, max_rows, C, ptr(g), ptr(b), eps,
              ptr(running_mean), ptr(running_var), momentum, act, ptr(mean), ptr(rstd), ptr(y), _ffi.dtype_code(x.dtype),
              stream())
-        ctx.save_for_backward(x, y, mean, rstd, g, seg_off, row_seg)
+        ctx.save_for_backward(x, y, mean, rstd, g, seg_off, row_seg)   # None entries are allowed
         ctx.meta = (S, max_rows, act, res is not None, gamma.shape if gamma is not None else None,
                     beta.shape if beta is not None else None)
         return y
@@ -383,13 +394,13 @@ def norm_apply_eval(x, mean, var, gamma, beta, eps, act=ACT_NONE, res=None):
 class SparseTensor:
 
     def __init__(self, features: torch.Tensor, coordinates: Optional[torch.Tensor] = None, coordinate_map_key=None,
-                 coordinate_manager: Optional[CoordinateManager] = None):
+                 coordinate_manager: Optional[CoordinateManager] = None, batch_size: Optional[int] = None):
         if coordinates is not None:
             assert coordinate_map_key is None
             if coordinate_manager is None:
                 coordinate_manager = CoordinateManager(features.device)
             coords = coordinates.to(device=features.device, dtype=torch.int32)
-            key, in2out = coordinate_manager.insert(coords, 1)
+            key, in2out = coordinate_manager.insert(coords, 1, batch_size)
             n = coordinate_manager.maps[key].n
             # first occurrence wins: scatter in reverse order so the lowest row index is written last
             first = torch.full((n, ), coords.shape[0], dtype=torch.int64, device=features.device)
@@ -594,10 +605,8 @@ class MinkowskiBatchNorm(nn.Module):
 def batch_norm_rows(f, bn: nn.BatchNorm1d, training: bool, act=ACT_NONE, res=None):
     if training:
         N = f.shape[0]
-        seg_off = torch.tensor([0, N], dtype=torch.int32, device=f.device)
-        with torch.no_grad():
-            bn.num_batches_tracked += 1
-        return seg_norm(f, bn.weight, bn.bias, seg_off, None, 1, N, bn.eps, act, res, bn.running_mean, bn.running_var,
+        # (num_batches_tracked is only read when momentum is None; it is advanced once per step by the optimiser wrapper)
+        return seg_norm(f, bn.weight, bn.bias, None, None, 1, N, bn.eps, act, res, bn.running_mean, bn.running_var,
                         bn.momentum)
     return norm_apply_eval(f, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.eps, act, res)
 

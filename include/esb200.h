@@ -58,10 +58,11 @@ int esb_spconv_fwd(const void* x, const void* w, const int* nbr, void* y, long l
 int esb_spconv_wgrad(const void* x, const void* dy, const int* pair_in, const int* pair_out, const int* k_offsets,
                      float* dw, long long n_pairs_hint, int cin, int cout, int K, int dtype, void* stream);
 
-/* bf16 tensor-core (tcgen05/TMEM) path of the same operator; wt = W_k^T (K,cout,cin); masks from esb_kmap_tile_masks */
+/* bf16 tensor-core (tcgen05/TMEM) path of the same operator; masks from esb_kmap_tile_masks;
+ * w_layout 0: w (K,cout,cin), 1: w (K,cin,cout) — forward and dgrad read the SAME stored bf16 kernel, no transpose */
 int esb_kmap_tile_masks(const int* nbr, int K, long long n, unsigned* masks, void* stream);
 int esb_spconv_tc_fwd(const void* x, const void* wt, const int* nbr, const unsigned* masks, void* y, long long n_out,
-                      int cin, int cout, int K, void* stream);
+                      int cin, int cout, int K, int w_layout, void* stream);
 int esb_spconv_tc_wgrad(const void* x, const void* dy, const int* pair_in, const int* pair_out, const int* k_offsets,
                         float* dw, long long n_pairs_hint, int cin, int cout, int K, void* stream);
 
@@ -93,14 +94,15 @@ int esb_paint_bwd(const int* coords, long long N, float voxel_size, const void* 
 
 /* ---- FCAF3D head: target assignment (fcaf3d_head.py:1578-1664) and sigmoid focal loss (mmcv.ops.sigmoid_focal_loss
  * through mmdet.FocalLoss, cfg :46-52) --------------------------------------------------------------------------- */
-size_t esb_fcaf3d_targets_workspace_bytes(int L, int Ng);
-int esb_fcaf3d_targets(const float* points, const int* level_off, int L, int Np, const float* boxes, const float* rneg,
-                       const long long* labels, int Ng, int assign_thr, int center_thr, float* center_t, float* bbox_t,
-                       long long* cls_t, int* box_idx, void* ws, size_t ws_bytes, void* stream);
+size_t esb_fcaf3d_targets_workspace_bytes(int L, int NgT, int B);
+int esb_fcaf3d_targets(const float* points, const int* level_off, int L, int Np, const int* pt_batch,
+                       const float* boxes, const float* rneg, const long long* labels, const int* box_off, int B, int NgT,
+                       int max_ng, int assign_thr, int center_thr, float* center_t, float* bbox_t, long long* cls_t,
+                       int* box_idx, void* ws, size_t ws_bytes, void* stream);
 int esb_focal_loss_fwd(const void* logits, const long long* target, long long n, int C, float gamma, float alpha,
-                       float* loss_sum, int dtype, void* stream);
+                       const float* row_w, float* loss_sum, int dtype, void* stream);
 int esb_focal_loss_bwd(const void* logits, const long long* target, long long n, int C, float gamma, float alpha,
-                       const float* scale_dev, void* grad, int dtype, void* stream);
+                       const float* row_w, const float* scale_dev, void* grad, int dtype, void* stream);
 
 /* ---- rotated BEV IoU + NMS (mmcv.ops.nms3d / nms3d_normal; fcaf3d_head.py:1666-1725) ---------------------------- */
 int esb_nms_bev_segmented(const float* boxes, const int* seg_off, int S, int max_seg, float iou_thr, int rotated,

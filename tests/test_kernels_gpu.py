@@ -292,6 +292,43 @@ def test_fcaf3d_targets_bit_exact(seed):
     assert torch.equal(ct.cpu()[~pos] >= 0, ct_r[~pos] >= 0)
 
 
+def test_fcaf3d_targets_batched_matches_per_scan_oracle():
+    """Two scans with interleaved rows (the natural order after a coordinate union) in ONE kernel pipeline."""
+    from embodiedscan_b200.dense_heads import fcaf3d_targets_batched
+    from oracle import model_ref as M
+    scenes = [_head_scene(0), _head_scene(1, n_pts=(5000, 1200, 300, 90))]
+    g = torch.Generator().manual_seed(9)
+    pts_all, batch_all, sizes, back = [], [], [], []
+    for l in range(4):
+        p = torch.cat([scenes[0][0][l], scenes[1][0][l]])
+        b = torch.cat([torch.zeros(len(scenes[0][0][l]), dtype=torch.int32), torch.ones(len(scenes[1][0][l]), dtype=torch.int32)])
+        # keep the relative order of each scan's rows (ties break by row index): stable re-sort inside the interleave
+        keys = torch.rand(len(p), generator=g)
+        order = torch.argsort(keys)
+        slots0 = order[: len(scenes[0][0][l])].sort().values
+        slots1 = order[len(scenes[0][0][l]):].sort().values
+        pl = torch.empty_like(p)
+        bl = torch.empty_like(b)
+        pl[slots0], bl[slots0] = scenes[0][0][l], 0
+        pl[slots1], bl[slots1] = scenes[1][0][l], 1
+        pts_all.append(pl); batch_all.append(bl); sizes.append(len(pl)); back.append((slots0, slots1))
+    ct, bt, kt = fcaf3d_targets_batched(torch.cat(pts_all).to(_dev()), sizes, torch.cat(batch_all).to(_dev()),
+                                        [scenes[0][1].to(_dev()), scenes[1][1].to(_dev())],
+                                        [scenes[0][2].to(_dev()), scenes[1][2].to(_dev())], 27, 18)
+    ct, bt, kt = ct.cpu(), bt.cpu(), kt.cpu()
+    for sidx in range(2):
+        ct_r, bt_r, kt_r = M.get_targets(scenes[sidx][0], scenes[sidx][1], scenes[sidx][2])
+        off_b, off_r = 0, 0
+        for l in range(4):
+            sl = back[l][sidx] + off_b
+            n = len(scenes[sidx][0][l])
+            assert torch.equal(kt[sl], kt_r[off_r:off_r + n]) and torch.equal(bt[sl], bt_r[off_r:off_r + n])
+            pos = kt_r[off_r:off_r + n] >= 0
+            assert float((ct[sl][pos] - ct_r[off_r:off_r + n][pos]).abs().max() if pos.any() else 0.) < 1e-5
+            off_b += sizes[l]
+            off_r += n
+
+
 def test_targets_no_boxes():
     from embodiedscan_b200.dense_heads import fcaf3d_targets
     pts, _, _ = _head_scene(0)
