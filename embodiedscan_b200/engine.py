@@ -14,6 +14,9 @@ import torch.nn as nn
 from ._ffi import call, ptr, stream
 
 
+ALIGN = 16   # elements
+
+
 class FlatArena:
     """All trainable parameters live in ONE contiguous fp32 buffer, their gradients in another (same offsets)."""
 
@@ -26,7 +29,7 @@ class FlatArena:
         offs, n = [], 0
         for p in params:
             offs.append(n)
-            n += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned
+            n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN     # 64 B in fp32, 32 B in the bf16 shadow (16 B cp.async loads)
         self.numel = n
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -45,7 +48,7 @@ class FlatArena:
         start, cur = 0, 0
         per = max(bucket_bytes // 4, 1)
         for i, (p, o) in enumerate(zip(params, offs)):
-            end = o + (p.numel() + 3) // 4 * 4
+            end = o + (p.numel() + ALIGN - 1) // ALIGN * ALIGN
             self.bucket_of.append(len(self.buckets))
             if end - start >= per or i == len(params) - 1:
                 self.buckets.append((start, end))
