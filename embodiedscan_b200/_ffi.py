@@ -37,6 +37,8 @@ SIGNATURES = {
     'esb_norm_apply': ('pppqippppipip', 'i'),
     'esb_norm_bwd': ('pppppiqiipppippppip', 'i'),
     'esb_act_fwd': ('ppqiip', 'i'),
+    'esb_bias_act_fwd': ('ppppqiiip', 'i'),
+    'esb_act_bwd': ('pppqiip', 'i'),
     'esb_paint_meta_bytes': ('', 'i'),
     'esb_paint_fwd': ('pqfppipiiiffppip', 'i'),
     'esb_paint_bwd': ('pqfppipiiiffpip', 'i'),

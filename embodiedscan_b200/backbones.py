@@ -89,6 +89,38 @@ def _fold(conv_w, bn: nn.BatchNorm2d, dtype):
     return w.to(dtype), b.to(dtype)
 
 
+class _BiasResAct(torch.autograd.Function):
+    """y = act(conv_out + bias[c] (+ res)) in ONE pass over the NHWC activation, written in place of conv_out."""
+
+    @staticmethod
+    def forward(ctx, conv_out, bias, res, act):
+        from . import _ffi
+        assert conv_out.is_contiguous(memory_format=torch.channels_last)
+        N, C, H, W = conv_out.shape
+        if res is not None and not res.is_contiguous(memory_format=torch.channels_last):
+            res = res.contiguous(memory_format=torch.channels_last)
+        _ffi.call('esb_bias_act_fwd', conv_out.data_ptr(), bias.data_ptr(), _ffi.ptr(res), conv_out.data_ptr(), N * H * W, C,
+                  act, _ffi.dtype_code(conv_out.dtype), _ffi.stream())
+        ctx.mark_dirty(conv_out)
+        ctx.act, ctx.has_res = act, res is not None
+        if act != SP.ACT_NONE:
+            ctx.save_for_backward(conv_out)
+        return conv_out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _ffi
+        if ctx.act != SP.ACT_NONE:
+            (y, ) = ctx.saved_tensors
+            dy = dy.contiguous(memory_format=torch.channels_last)
+            g = torch.empty_like(y)
+            _ffi.call('esb_act_bwd', dy.data_ptr(), y.data_ptr(), g.data_ptr(), y.numel(), ctx.act,
+                      _ffi.dtype_code(y.dtype), _ffi.stream())
+        else:
+            g = dy
+        return g, None, (g if ctx.has_res else None), None
+
+
 class _ConvBN(nn.Module):
     """Conv2d(bias=False) followed by a BatchNorm2d; evaluated folded when the norm is in eval mode."""
 
@@ -97,20 +129,27 @@ class _ConvBN(nn.Module):
         self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
         self.bn = nn.BatchNorm2d(cout)
 
-    def forward(self, x, relu):
+    def forward(self, x, relu, res=None):
         if x.dtype == torch.float32 and x.is_cuda and torch.backends.cudnn.allow_tf32:
             # fp32 is the parity arithmetic: keep cuDNN out of TF32 (10-bit mantissa breaks the 1e-3 bound)
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                return self._forward(x, relu)
-        return self._forward(x, relu)
+                return self._forward(x, relu, res)
+        return self._forward(x, relu, res)
 
-    def _forward(self, x, relu):
+    def _forward(self, x, relu, res):
         conv, bn = self.conv, self.bn
         if bn.training:
             y = bn(F.conv2d(x, conv.weight.to(x.dtype), None, conv.stride, conv.padding))
-        else:
-            w, b = _fold(conv.weight, bn, x.dtype)
-            y = F.conv2d(x, w, b, conv.stride, conv.padding)
+            y = y + res if res is not None else y
+            return F.relu(y, inplace=True) if relu else y
+        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+        w = (conv.weight * scale[:, None, None, None]).to(x.dtype)
+        b = (bn.bias - bn.running_mean * scale).float()
+        y = F.conv2d(x, w, None, conv.stride, conv.padding)
+        if y.is_cuda and y.shape[1] % 8 == 0 and y.is_contiguous(memory_format=torch.channels_last):
+            return _BiasResAct.apply(y, b, res, SP.ACT_RELU if relu else SP.ACT_NONE)   # bias + residual + ReLU fused
+        y = y + b.to(y.dtype).view(1, -1, 1, 1)
+        y = y + res if res is not None else y
         return F.relu(y, inplace=True) if relu else y
 
 
@@ -126,8 +165,7 @@ class _Bottleneck2D(nn.Module):
 
     def forward(self, x):
         idt = self.ds(x, False) if self.ds is not None else x
-        out = self.cb3(self.cb2(self.cb1(x, True), True), False)
-        return F.relu(out + idt, inplace=True)
+        return self.cb3(self.cb2(self.cb1(x, True), True), True, res=idt)
 
 
 class _BasicBlock2D(nn.Module):
@@ -141,8 +179,7 @@ class _BasicBlock2D(nn.Module):
 
     def forward(self, x):
         idt = self.ds(x, False) if self.ds is not None else x
-        out = self.cb2(self.cb1(x, True), False)
-        return F.relu(out + idt, inplace=True)
+        return self.cb2(self.cb1(x, True), True, res=idt)
 
 
 # state_dict names follow mmdet/torchvision: conv1/bn1, layer{i}.{j}.conv{k}/bn{k}, downsample.0/.1

@@ -88,15 +88,17 @@ __global__ void best_level_kernel(const int* __restrict__ counts, int L, int Ng,
 // Boxes with more than TOPK_CAP candidates fall back to rescanning the level each round.
 constexpr int TOPK_CAP = 4096;
 
-__global__ void __launch_bounds__(256)
+constexpr int TOPK_THREADS = 1024;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
 topk_threshold_kernel(const float* __restrict__ pts, const int* __restrict__ level_off, const int* __restrict__ pt_batch,
                       const int* __restrict__ n_pts_of_scan, const float* __restrict__ boxes,
                       const float* __restrict__ rneg, const int* __restrict__ box_off, int B,
                       const int* __restrict__ best, int kth, float* __restrict__ top) {
   __shared__ float c_val[TOPK_CAP];
   __shared__ int c_idx[TOPK_CAP];
-  __shared__ float s_val[256];
-  __shared__ int s_idx[256];
+  __shared__ float s_val[TOPK_THREADS];
+  __shared__ int s_idx[TOPK_THREADS];
   __shared__ float prev_v;
   __shared__ int prev_i;
   __shared__ int n_cand;
@@ -110,7 +112,7 @@ topk_threshold_kernel(const float* __restrict__ pts, const int* __restrict__ lev
   const int k_eff = min(kth, n_pts_of_scan[scan]);
   if (tid == 0) { prev_v = INFINITY; prev_i = -1; n_cand = 0; }
   __syncthreads();
-  for (int p = p_beg + tid; p < p_end; p += 256) {
+  for (int p = p_beg + tid; p < p_end; p += TOPK_THREADS) {
     if (pt_batch && pt_batch[p] != scan) continue;
     FaceDist f = face_distances(box, R, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
     if (!inside_box(f)) continue;
@@ -130,14 +132,14 @@ topk_threshold_kernel(const float* __restrict__ pts, const int* __restrict__ lev
     const float pv = prev_v;
     const int pi = prev_i;
     if (in_smem) {
-      for (int c = tid; c < nc; c += 256) {
+      for (int c = tid; c < nc; c += TOPK_THREADS) {
         float v = c_val[c];
         int p = c_idx[c];
         bool after = (v < pv) || (v == pv && p > pi);
         if (after && (bi < 0 || v > bv || (v == bv && p < bi))) { bv = v; bi = p; }
       }
     } else {
-      for (int p = p_beg + tid; p < p_end; p += 256) {
+      for (int p = p_beg + tid; p < p_end; p += TOPK_THREADS) {
         if (pt_batch && pt_batch[p] != scan) continue;
         FaceDist f = face_distances(box, R, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
         if (!inside_box(f)) continue;
@@ -149,7 +151,7 @@ topk_threshold_kernel(const float* __restrict__ pts, const int* __restrict__ lev
     s_val[tid] = bv;
     s_idx[tid] = bi;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = TOPK_THREADS / 2; s > 0; s >>= 1) {
       if (tid < s) {
         float ov = s_val[tid + s];
         int oi = s_idx[tid + s];
@@ -165,10 +167,18 @@ topk_threshold_kernel(const float* __restrict__ pts, const int* __restrict__ lev
 }
 
 // number of points of each scan (torch.topk's `min(k+1, len(centerness))` uses the scan's total point count)
-__global__ void count_scan_points_kernel(const int* __restrict__ pt_batch, int Np, int* __restrict__ n_pts_of_scan) {
+__global__ void count_scan_points_kernel(const int* __restrict__ pt_batch, int Np, int B, int* __restrict__ n_pts_of_scan) {
+  __shared__ int hist[64];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= Np) return;
-  atomicAdd(&n_pts_of_scan[pt_batch ? pt_batch[p] : 0], 1);
+  if (p < Np) {
+    int b = pt_batch ? pt_batch[p] : 0;
+    if (b < 64) atomicAdd(&hist[b], 1); else atomicAdd(&n_pts_of_scan[b], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < min(B, 64); i += blockDim.x)
+    if (hist[i]) atomicAdd(&n_pts_of_scan[i], hist[i]);
 }
 
 // per point: min-volume box among (inside & best level & centerness > top[g]) over the boxes of its scan;
@@ -298,9 +308,9 @@ extern "C" int esb_fcaf3d_targets(const float* points, const int* level_off, int
     ESB_CUDA_CALL(cudaMemsetAsync(n_pts_of_scan, 0, (size_t)B * 4, stream));
     dim3 g1(esb_div_up(Np, 256), max_ng > 0 ? max_ng : 1);
     count_inside_kernel<<<g1, 256, 0, stream>>>(points, level_off, L, Np, pt_batch, boxes, rneg, box_off, NgT, counts);
-    count_scan_points_kernel<<<esb_div_up(Np, 256), 256, 0, stream>>>(pt_batch, Np, n_pts_of_scan);
+    count_scan_points_kernel<<<esb_div_up(Np, 1024), 1024, 0, stream>>>(pt_batch, Np, B, n_pts_of_scan);
     best_level_kernel<<<esb_div_up(NgT, 128), 128, 0, stream>>>(counts, L, NgT, assign_thr, best);
-    topk_threshold_kernel<<<NgT, 256, 0, stream>>>(points, level_off, pt_batch, n_pts_of_scan, boxes, rneg, box_off, B,
+    topk_threshold_kernel<<<NgT, TOPK_THREADS, 0, stream>>>(points, level_off, pt_batch, n_pts_of_scan, boxes, rneg, box_off, B,
                                                     best, center_thr + 1, top);
   }
   assign_kernel<<<esb_div_up(Np, 128), 128, 0, stream>>>(points, level_off, L, Np, pt_batch, boxes, rneg, labels, box_off,

@@ -144,6 +144,7 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+  __shared__ int idx_s[2][TC_M];
 
   const int warp = threadIdx.x >> 5;
   const int tile = blockIdx.x;
@@ -168,24 +169,40 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 
   if (warp < 4) {
     // ---------------- producers ----------------
-    const int r = threadIdx.x;                       // tile row owned by this thread
-    const int row = tile * TC_M + r;
-    const uint32_t a_row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-    const uint32_t sw = (uint32_t)(r & 7);
-    int it = 0;
-    for (uint32_t mk = mask; mk; mk &= mk - 1) {
+    // Lane mapping: 8 consecutive lanes fetch the 8 x 16 B chunks of ONE gathered row, so a warp-wide cp.async touches
+    // 4 rows x 128 B (4 L1 wavefronts) instead of 32 different rows (32 wavefronts: the round-1a L1TEX bottleneck).
+    // Thread t owns chunk (t & 7) of rows (t >> 3) + 16 i, i = 0..7; r & 7 == (t >> 3) & 7 for all of them.
+    const int t = threadIdx.x;
+    const int sub = t & 7, rgrp = t >> 3;
+    const uint32_t sw = (uint32_t)(rgrp & 7);
+    const uint32_t a_thread_off = (uint32_t)((rgrp >> 3) * 1024 + (rgrp & 7) * 128) + ((sub ^ sw) << 4);
+    int it = 0, kcount = 0;
+    const int my_row = tile * TC_M + t;
+    // the neighbour index of the NEXT offset is loaded while the stages of the current one are in flight
+    int v_next = (mask && my_row < n_out) ? nbr[(long long)(__ffs(mask) - 1) * n_out + my_row] : -1;
+    for (uint32_t mk = mask; mk; mk &= mk - 1, ++kcount) {
       const int k = __ffs(mk) - 1;
-      const int src = row < n_out ? nbr[(long long)k * n_out + row] : -1;
-      const __nv_bfloat16* xrow = x + (long long)(src >= 0 ? src : 0) * cin;
-      const int nbytes = src >= 0 ? 16 : 0;
+      int* idx_buf = idx_s[kcount & 1];
+      idx_buf[t] = v_next;
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // producers only (warps 0-3)
+      {
+        const uint32_t rest = mk & (mk - 1);
+        v_next = (rest && my_row < n_out) ? nbr[(long long)(__ffs(rest) - 1) * n_out + my_row] : -1;
+      }
+      int src[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) src[i] = idx_buf[rgrp + 16 * i];
       const __nv_bfloat16* wk = B_MN ? wt + (long long)k * cin * cout + n0 : wt + ((long long)k * cout + n0) * cin;
       for (int c = 0; c < nchunk; ++c, ++it) {
         const int s = it % STAGES;
         if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES) + a_row_off;
+        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES) + a_thread_off;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cp_async16_ca(a_base + ((j ^ sw) << 4), xrow + c * TC_BK + j * 8, nbytes);
+        for (int i = 0; i < 8; ++i)
+          cp_async16_ca(a_base + i * 2048, x + (long long)(src[i] >= 0 ? src[i] : 0) * cin + c * TC_BK + sub * 8,
+                        src[i] >= 0 ? 16 : 0);
         const uint32_t b_base = smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES);
+        const int r = t;
 #pragma unroll
         for (int q = 0; q < N_TILE / 16; ++q) {
           const int idx = q * 128 + r;
@@ -213,6 +230,7 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     for (int d = (total > LAG ? total - LAG : 0); d < total; ++d) mbar_arrive(&full_bar[d % STAGES]);
 
     // ---------------- epilogue ----------------
+    const int row = tile * TC_M + threadIdx.x;       // TMEM lane = tile row
     if (total > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
@@ -278,7 +296,8 @@ template <int N_TILE, int STAGES>
 __global__ void __launch_bounds__(160)
 spconv_tc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                        const int* __restrict__ pair_in, const int* __restrict__ pair_out,
-                       const int* __restrict__ k_offsets, float* __restrict__ dw, int cin, int cout, int splits) {
+                       const int* __restrict__ k_offsets, float* __restrict__ dw, int cin, int cout, int K,
+                       int chunk_pairs) {
   constexpr int A_BYTES = 64 * 256;              // 64 pairs x 128 channels (2 M-atoms of 64 ch)
   constexpr int B_BYTES = 64 * N_TILE * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -292,15 +311,21 @@ spconv_tc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
 
   const int warp = threadIdx.x >> 5;
-  const int k = blockIdx.x / splits, sp = blockIdx.x - k * splits;
+  // Work item = one chunk of `chunk_pairs` consecutive pairs of ONE offset (uniform work per CTA: no heavy-offset tail).
+  // blockIdx.x enumerates chunks offset by offset; CTAs past the last chunk exit.
+  int k = 0, chunk = blockIdx.x, p_beg = 0, p_end = 0;
+  for (; k < K; ++k) {
+    p_beg = k_offsets[k];
+    p_end = k_offsets[k + 1];
+    const int nch = (p_end - p_beg + chunk_pairs - 1) / chunk_pairs;
+    if (chunk < nch) break;
+    chunk -= nch;
+  }
+  if (k >= K) return;                              // uniform for the whole CTA
   const int ci0 = blockIdx.y * 128, co0 = blockIdx.z * N_TILE;
-  const int p_beg = k_offsets[k], p_end = k_offsets[k + 1];
-  const int np = p_end - p_beg;
-  const int per = ((np + splits - 1) / splits + 63) / 64 * 64;
-  const int s_beg = p_beg + sp * per;
-  const int s_end = min(p_end, s_beg + per);
-  const int total = s_end > s_beg ? (s_end - s_beg + 63) / 64 : 0;
-  if (total == 0) return;                          // uniform for the whole CTA
+  const int s_beg = p_beg + chunk * chunk_pairs;
+  const int s_end = min(p_end, s_beg + chunk_pairs);
+  const int total = (s_end - s_beg + 63) / 64;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -319,34 +344,55 @@ spconv_tc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
 
   if (warp < 4) {
     const int t = threadIdx.x;
+    // thread t moves chunk (t & 15) of pair rows kk = (t >> 4) + 8 q, q = 0..7 (16 consecutive lanes = one 256 B row);
+    // the pair indices of stage it+1 are fetched while the copies of stage it are in flight (index-load latency was
+    // 55% of the stall samples in the round-1a profile).
+    const int mc = t & 15, kk0 = t >> 4;
+    const bool a_ok_ch = mc * 8 < a_ch;
+    int ri[8], ro[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int p = s_beg + kk0 + 8 * q;
+      ri[q] = p < s_end ? pair_in[p] : -1;
+      ro[q] = p < s_end ? pair_out[p] : -1;
+    }
     for (int it = 0; it < total; ++it) {
       const int s = it % STAGES;
       if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-      const int p0 = s_beg + it * 64;
       const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
       const uint32_t b_base = a_base + A_BYTES;
-      // A: 64 pairs x 16 chunks(16B) ; canonical MN-major SW128: atom(mi, kj) at mi*8192 + kj*1024, row kk%8, chunk^row
+      // canonical MN-major SW128: atom(mi, kj) at mi*8192 + kj*1024, row kk%8, 16 B chunk index ^ row
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int idx = q * 128 + t;
-        const int kk = idx >> 4, mc = idx & 15;
-        const int p = p0 + kk;
-        const bool ok = p < s_end && mc * 8 < a_ch;
-        const int ri = ok ? pair_in[p] : 0;
+        const int kk = kk0 + 8 * q;
+        const bool ok = ri[q] >= 0 && a_ok_ch;
         const uint32_t dst = a_base + (mc >> 3) * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + (((mc & 7) ^ (kk & 7)) << 4);
-        cp_async16_ca(dst, x + (long long)ri * cin + ci0 + mc * 8, ok ? 16 : 0);
+        cp_async16_cg(dst, x + (long long)(ok ? ri[q] : 0) * cin + ci0 + mc * 8, ok ? 16 : 0);
       }
 #pragma unroll
       for (int q = 0; q < N_TILE / 16; ++q) {
         const int idx = q * 128 + t;
         const int kk = idx / (N_TILE / 8), nc = idx % (N_TILE / 8);
-        const int p = p0 + kk;
-        const bool ok = p < s_end;
-        const int ro = ok ? pair_out[p] : 0;
+        // N_TILE = 128: kk = kk0 + 8 q (register ro[q]); N_TILE = 64: kk = (t >> 3) + 16 q -> fetch through ro when aligned
+        int rr;
+        if (N_TILE == 128) {
+          rr = ro[q];
+        } else {
+          const int p = s_beg + it * 64 + kk;
+          rr = p < s_end ? pair_out[p] : -1;
+        }
         const uint32_t dst = b_base + (nc >> 3) * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + (((nc & 7) ^ (kk & 7)) << 4);
-        cp_async16_ca(dst, dy + (long long)ro * cout + co0 + nc * 8, ok ? 16 : 0);
+        cp_async16_cg(dst, dy + (long long)(rr >= 0 ? rr : 0) * cout + co0 + nc * 8, rr >= 0 ? 16 : 0);
       }
       cp_async_commit();
+      if (it + 1 < total) {   // prefetch the next stage's pair indices
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int p = s_beg + (it + 1) * 64 + kk0 + 8 * q;
+          ri[q] = p < s_end ? pair_in[p] : -1;
+          ro[q] = p < s_end ? pair_out[p] : -1;
+        }
+      }
       if (it >= LAG) {
         cp_async_wait<LAG>();
         fence_proxy_async();
@@ -417,14 +463,14 @@ int launch_fwd(const void* x, const void* wt, const int* nbr, const unsigned* ma
 
 template <int N_TILE, int STAGES>
 int launch_wgrad(const void* x, const void* dy, const int* pin, const int* pout, const int* koff, float* dw, int cin,
-                 int cout, int K, int splits, cudaStream_t stream) {
+                 int cout, int K, int n_chunks, int chunk_pairs, cudaStream_t stream) {
   size_t smem = (size_t)STAGES * (64 * 256 + 64 * N_TILE * 2) + 1024 + 256;
   auto kern = spconv_tc_wgrad_kernel<N_TILE, STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { esb_set_error("spconv_tc_wgrad: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
-  dim3 grid(K * splits, esb_div_up(cin, 128), cout / N_TILE);
-  kern<<<grid, 160, smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, pin, pout, koff, dw, cin, cout,
-                                    splits);
+  dim3 grid(n_chunks, esb_div_up(cin, 128), cout / N_TILE);
+  kern<<<grid, 160, smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, pin, pout, koff, dw, cin, cout, K,
+                                    chunk_pairs);
   return ESB_OK;
 }
 
@@ -474,15 +520,18 @@ extern "C" int esb_spconv_tc_wgrad(const void* x, const void* dy, const int* pai
   cudaStream_t stream = (cudaStream_t)stream_;
   ESB_CHECK_ARG(cin % 64 == 0 && cout % 64 == 0 && cin > 0 && cout > 0, "esb_spconv_tc_wgrad: channels must be multiples of 64");
   int n_tile = (cout % 128 == 0) ? 128 : 64;
-  int ctas_per_split = K * esb_div_up(cin, 128) * (cout / n_tile);
-  long long per_k = n_pairs_hint / K + 1;
-  int splits = (int)(2 * 148 / ctas_per_split);
-  int max_by_pairs = (int)(per_k / 512) + 1;
-  if (splits > max_by_pairs) splits = max_by_pairs;
-  if (splits < 1) splits = 1;
-  if (splits > 64) splits = 64;
-  int rc = n_tile == 128 ? launch_wgrad<128, 3>(x, dy, pair_in, pair_out, k_offsets, dw, cin, cout, K, splits, stream)
-                         : launch_wgrad<64, 4>(x, dy, pair_in, pair_out, k_offsets, dw, cin, cout, K, splits, stream);
+  // n_pairs_hint is an upper bound of the pair count (K * n_out); aim at ~4 waves of 2 CTAs/SM over the channel tiles
+  long long tiles = (long long)esb_div_up(cin, 128) * (cout / n_tile);
+  long long target_chunks = (4LL * 296 + tiles - 1) / tiles;
+  long long cp = (n_pairs_hint / 2 + target_chunks - 1) / target_chunks;   // maps are ~40% dense: hint/2 ~ real pairs
+  cp = (cp + 63) / 64 * 64;
+  if (cp < 512) cp = 512;
+  if (cp > 16384) cp = 16384;
+  int chunk_pairs = (int)cp;
+  int n_chunks = (int)(n_pairs_hint / chunk_pairs) + K + 1;               // upper bound; surplus CTAs exit immediately
+  int rc = n_tile == 128
+               ? launch_wgrad<128, 3>(x, dy, pair_in, pair_out, k_offsets, dw, cin, cout, K, n_chunks, chunk_pairs, stream)
+               : launch_wgrad<64, 4>(x, dy, pair_in, pair_out, k_offsets, dw, cin, cout, K, n_chunks, chunk_pairs, stream);
   if (rc != ESB_OK) return rc;
   ESB_CUDA_LAUNCH_CHECK("spconv_tc_wgrad_kernel");
   return ESB_OK;

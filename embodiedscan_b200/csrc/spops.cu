@@ -204,6 +204,56 @@ __global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long 
   if (t < n) y[t] = esb_from_float<T>(act_fwd(esb_to_float<T>(x[t]), act));
 }
 
+// y = act(x + bias[c] + res) over (rows, C) row-major (an NHWC activation is exactly that), 8 channels per thread.
+// Replaces cuDNN's broadcast bias add + the separate residual add + ReLU of the folded conv+BN blocks (3 passes -> 1).
+template <typename T>
+__global__ void bias_act_kernel(const T* __restrict__ x, const float* __restrict__ bias, const T* __restrict__ res,
+                                T* __restrict__ y, long long n_vec, int C, int act) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_vec) return;
+  const int cv = C / 8;
+  const int c0 = (int)(t % cv) * 8;
+  float v[8], r[8];
+  if (sizeof(T) == 2) {
+    uint4 raw = reinterpret_cast<const uint4*>(x)[t];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    if (res) {
+      uint4 rr = reinterpret_cast<const uint4*>(res)[t];
+      const __nv_bfloat162* g = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { r[2 * i] = __low2float(g[i]); r[2 * i + 1] = __high2float(g[i]); }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = esb_to_float<T>(x[t * 8 + i]); r[i] = res ? esb_to_float<T>(res[t * 8 + i]) : 0.f; }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = act_fwd(v[i] + (bias ? bias[c0 + i] : 0.f) + (res ? r[i] : 0.f), act);
+  if (sizeof(T) == 2) {
+    uint4 o;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    reinterpret_cast<uint4*>(y)[t] = o;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[t * 8 + i] = esb_from_float<T>(v[i]);
+  }
+}
+
+// dx = dy * act'(y) expressed through the OUTPUT y (8 elements per thread)
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n,
+                               int act) {
+  long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (t + i < n)
+      dx[t + i] = esb_from_float<T>(esb_to_float<T>(dy[t + i]) * act_bwd_from_out(esb_to_float<T>(y[t + i]), act));
+}
+
 }  // namespace
 
 #define DISPATCH_T(dtype, ...)                         \
@@ -301,5 +351,25 @@ extern "C" int esb_act_fwd(const void* x, void* y, long long n, int act, int dty
   if (n == 0) return ESB_OK;
   DISPATCH_T(dtype, (act_fwd_kernel<T><<<esb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n, act)));
   ESB_CUDA_LAUNCH_CHECK("act_fwd_kernel");
+  return ESB_OK;
+}
+
+// y = act(x + bias[c] + res), x/res/y (rows, C) row-major with C % 8 == 0; y may alias x. bias fp32 (C) or NULL.
+extern "C" int esb_bias_act_fwd(const void* x, const float* bias, const void* res, void* y, long long rows, int C, int act,
+                                int dtype, void* stream) {
+  ESB_CHECK_ARG(C % 8 == 0, "esb_bias_act_fwd: C must be a multiple of 8");
+  long long n_vec = rows * (C / 8);
+  if (n_vec == 0) return ESB_OK;
+  DISPATCH_T(dtype, (bias_act_kernel<T><<<esb_div_up(n_vec, 256), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, bias, (const T*)res, (T*)y, n_vec, C, act)));
+  ESB_CUDA_LAUNCH_CHECK("bias_act_kernel");
+  return ESB_OK;
+}
+
+extern "C" int esb_act_bwd(const void* dy, const void* y, void* dx, long long n, int act, int dtype, void* stream) {
+  if (n == 0) return ESB_OK;
+  DISPATCH_T(dtype, (act_bwd_kernel<T><<<esb_div_up(n, 256 * 8), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dy, (const T*)y, (T*)dx, n, act)));
+  ESB_CUDA_LAUNCH_CHECK("act_bwd_kernel");
   return ESB_OK;
 }

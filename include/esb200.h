@@ -81,6 +81,10 @@ int esb_norm_bwd(const void* x, const void* y, const void* dy, const int* seg_of
                  long long N, int max_seg_rows, int C, const float* mean, const float* rstd, const float* gamma, int act,
                  float* sg, float* sgx, void* dx, void* dres, int dtype, void* stream);
 int esb_act_fwd(const void* x, void* y, long long n, int act, int dtype, void* stream);
+/* fused epilogue of the folded conv+BN blocks of the per-view 2D ResNet: y = act(x + bias[c] + res) on NHWC rows */
+int esb_bias_act_fwd(const void* x, const float* bias, const void* res, void* y, long long rows, int C, int act,
+                     int dtype, void* stream);
+int esb_act_bwd(const void* dy, const void* y, void* dx, long long n, int act, int dtype, void* stream);
 
 /* ---- point painting (batch_point_sample + apply_3d_transformation + batch_points_cam2img + F.grid_sample;
  * embodiedscan/models/layers/fusion_layers/point_fusion.py:208-311, structures/bbox_3d/utils.py:289-332) -------- */
