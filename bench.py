@@ -97,7 +97,7 @@ class ClockSampler(threading.Thread):
                                       ('sw_power_cap', 0x4)):
                         if r & bit:
                             self.reasons_seen.add(name)
-                    time.sleep(0.05)
+                    time.sleep(0.25)     # NVML queries contend with the CUDA driver lock: keep them sparse
                 else:
                     q = 'clocks.sm,clocks.max.sm'
                     out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
@@ -266,6 +266,19 @@ def main():
     for j in range(args.warmup):
         step(j)
         log(f'warmup step {j} done')
+    # roofline pass: the same K steps with a CUDA-event pair around every sparse-conv launch (on the launching
+    # stream), run BEFORE the timed region and kept out of `value` because ~1.7k event pairs per step cost host time in a host-bound step.
+    SP.CONV_PROFILE['records'].clear()
+    SP.CONV_PROFILE['enabled'] = True
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for j in range(args.steps):
+        step(args.warmup + j)
+    r1.record()
+    barrier()
+    SP.CONV_PROFILE['enabled'] = False
+    ms_roof = r0.elapsed_time(r1)
+    log('roofline pass done')
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -290,19 +303,6 @@ def main():
     launches = _ffi.launch_counter['kernels']
     value = world * args.batch * args.steps / (ms_total / 1000.0)
 
-    # roofline pass: the SAME K steps again with a CUDA-event pair around every sparse-conv launch (on the launching
-    # stream). Kept out of `value` because ~1.7k event pairs per step cost host time in a host-bound step.
-    SP.CONV_PROFILE['records'].clear()
-    SP.CONV_PROFILE['enabled'] = True
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r0.record()
-    for j in range(args.steps):
-        step(args.warmup + j)
-    r1.record()
-    barrier()
-    SP.CONV_PROFILE['enabled'] = False
-    ms_roof = r0.elapsed_time(r1)
-    log('roofline pass done')
 
     # roofline of the sparse-conv kernel (fwd + dgrad launches of spconv_fwd_kernel) from the events recorded above
     e = 2 if dtype == torch.bfloat16 else 4

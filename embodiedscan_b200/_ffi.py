@@ -46,6 +46,7 @@ SIGNATURES = {
     'esb_fcaf3d_targets': ('ppiippppp' + 'iiiii' + 'pppp' + 'pzp', 'i'),
     'esb_focal_loss_fwd': ('ppqiffppip', 'i'),
     'esb_focal_loss_bwd': ('ppqiffpppip', 'i'),
+    'esb_bbox_cd_loss': ('pppppippp', 'i'),
     'esb_nms_bev_segmented': ('ppiifipp', 'i'),
     'esb_iou_bev_pairwise': ('pipiipp', 'i'),
     'esb_img_normalize': ('piiiiippiipip', 'i'),

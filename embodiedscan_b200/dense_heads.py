@@ -6,6 +6,7 @@
   * the per-scan scalar ``reduce_mean(n_pos)`` calls are fused into ONE device-side vector all-reduce (no host sync);
   * the 284-iteration per-class NMS loop is one segmented kernel launch (csrc/nms.cu).
 """
+import ctypes
 from typing import List, Optional, Tuple
 
 import torch
@@ -100,6 +101,30 @@ class CrossEntropyLoss(nn.Module):
     def forward(self, pred, target, avg_factor):
         loss = F.binary_cross_entropy_with_logits(pred.float(), target.float(), reduction='none')
         return loss.sum() / avg_factor * self.loss_weight
+
+
+class _BBoxCD(torch.autograd.Function):
+    """Fused decode + decoupled corner-chamfer loss over the positives (csrc/head.cu::bbox_cd_loss_kernel): value and
+    the gradient w.r.t. the 12 regression channels in one launch; backward only scales the stored gradient."""
+
+    @staticmethod
+    def forward(ctx, points, bbox_pred, targets, row_w, weights):
+        P = bbox_pred.shape[0]
+        dev = bbox_pred.device
+        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        grad = torch.empty((P, 12), dtype=torch.float32, device=dev)
+        w4 = (ctypes.c_float * 4)(*[float(w) for w in weights])
+        call('esb_bbox_cd_loss', ptr(points.float().contiguous()), ptr(bbox_pred.float().contiguous()),
+             ptr(targets.float().contiguous()), ptr(row_w.float().contiguous()), ctypes.cast(w4, ctypes.c_void_p), P, ptr(loss),
+             ptr(grad), stream())
+        ctx.save_for_backward(grad)
+        ctx.dtype = bbox_pred.dtype
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad, ) = ctx.saved_tensors
+        return None, (grad * g).to(ctx.dtype), None, None, None
 
 
 def fcaf3d_targets_batched(points: torch.Tensor, level_sizes: List[int], pt_batch: Optional[torch.Tensor],
@@ -366,11 +391,20 @@ class FCAF3DHeadRotMat(nn.Module):
                                                      reduction='none')
             loss_center = (bce.squeeze(1) * w_pos).sum() * self.center_loss.loss_weight
             tgt = bbox_t[pos_inds]
-            decoded = self._bbox_pred_to_bbox(pts[pos_inds], pos_bbox_preds)
-            tgt_corners = bbox_to_corners(tgt)
             # per-scan mean over (P_scan x 8) corners, then mean over scans -> weight 1 / (8 * P_scan * B) per corner
             p_scan = n_pos_local[pb_all[pos_inds]]
             w_box = (1.0 / (8.0 * p_scan * B))[:, None]
+            fused = pos_bbox_preds.is_cuda and pos_bbox_preds.shape[1] == 12 and not self.norm_decouple_loss and \
+                (not self.decouple_bbox_loss or self.decouple_groups in (3, 4))
+            if fused:
+                if self.decouple_bbox_loss:
+                    wts = list(self.decouple_weights[:3]) + [self.decouple_weights[3] if self.decouple_groups == 4 else 0.]
+                else:
+                    wts = [0., 0., 0., 1.]
+                loss_bbox = _BBoxCD.apply(pts[pos_inds], pos_bbox_preds, tgt, w_box[:, 0] * self.bbox_loss.loss_weight, wts)
+                return dict(loss_center=loss_center, loss_bbox=loss_bbox, loss_cls=loss_cls)
+            decoded = self._bbox_pred_to_bbox(pts[pos_inds], pos_bbox_preds)
+            tgt_corners = bbox_to_corners(tgt)
 
             def cd(src):
                 return (chamfer_l1_src(bbox_to_corners(src), tgt_corners) * w_box).sum() * self.bbox_loss.loss_weight

@@ -341,8 +341,10 @@ class _SegNorm(torch.autograd.Function):
         mean = torch.empty((S, C), dtype=torch.float32, device=dev)
         rstd = torch.empty((S, C), dtype=torch.float32, device=dev)
         y = torch.empty_like(x)
-        g = gamma.detach().float().contiguous().view(-1) if gamma is not None else None
-        b = beta.detach().float().contiguous().view(-1) if beta is not None else None
+        g = gamma.detach() if gamma is not None else None      # fp32 contiguous parameters: used as is
+        b = beta.detach() if beta is not None else None
+        assert (g is None or (g.dtype == torch.float32 and g.is_contiguous())) and \
+            (b is None or (b.dtype == torch.float32 and b.is_contiguous()))
         resc = res.contiguous() if res is not None else None
         call('esb_norm_fwd', ptr(x), ptr(resc), ptr(seg_off), ptr(row_seg), S, N, max_rows, C, ptr(g), ptr(b), eps,
              ptr(running_mean), ptr(running_var), momentum, act, ptr(mean), ptr(rstd), ptr(y), _ffi.dtype_code(x.dtype),
@@ -364,8 +366,12 @@ class _SegNorm(torch.autograd.Function):
         dres = torch.empty_like(x) if has_res else None
         call('esb_norm_bwd', ptr(x), ptr(y), ptr(dy), ptr(seg_off), ptr(row_seg), S, N, max_rows, C, ptr(mean), ptr(rstd),
              ptr(g), act, ptr(sg), ptr(sgx), ptr(dx), ptr(dres), _ffi.dtype_code(x.dtype), stream())
-        dgamma = sgx.sum(0).view(gshape) if gshape is not None else None
-        dbeta = sg.sum(0).view(bshape) if bshape is not None else None
+        if S == 1:       # BatchNorm: the (1,C) sums ARE the parameter gradients (no reduction kernel)
+            dgamma = sgx.view(gshape) if gshape is not None else None
+            dbeta = sg.view(bshape) if bshape is not None else None
+        else:
+            dgamma = sgx.sum(0).view(gshape) if gshape is not None else None
+            dbeta = sg.sum(0).view(bshape) if bshape is not None else None
         return dx, dres, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 

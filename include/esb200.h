@@ -108,6 +108,11 @@ int esb_focal_loss_fwd(const void* logits, const long long* target, long long n,
 int esb_focal_loss_bwd(const void* logits, const long long* target, long long n, int C, float gamma, float alpha,
                        const float* row_w, const float* scale_dev, void* grad, int dtype, void* stream);
 
+/* box regression: _bbox_pred_to_bbox + 4 decoupled BBoxCDLoss terms (fcaf3d_head.py:1224-1281,1454-1525;
+ * chamfer_distance.py:160-285) for all positives, value and gradient in one launch */
+int esb_bbox_cd_loss(const float* points, const float* bbox_pred, const float* targets, const float* row_w,
+                     const float* w4_host, int P, float* loss_out, float* grad, void* stream);
+
 /* ---- rotated BEV IoU + NMS (mmcv.ops.nms3d / nms3d_normal; fcaf3d_head.py:1666-1725) ---------------------------- */
 int esb_nms_bev_segmented(const float* boxes, const int* seg_off, int S, int max_seg, float iou_thr, int rotated,
                           unsigned char* keep, void* stream);
