@@ -326,8 +326,15 @@ def main():
             n_rec += 1
     peak, peak_src = peaks()
     achieved = tot_bytes / (tot_ms / 1000.0) / 1e9 if tot_ms > 0 else 0.0
-    roofline = {'bound': 'hbm', 'kernel': 'spconv_fwd_kernel (forward + dgrad launches)', 'achieved': achieved,
-                'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get('spconv_tc_fwd_kernel')
+        if tj:
+            traffic, traffic_note = tj['dram_bytes_per_launch_avg'], tj['source']
+    roofline = {'bound': 'hbm', 'kernel': 'spconv_tc_fwd_kernel (tcgen05; forward + dgrad launches)', 'achieved': achieved,
+                'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_note': traffic_note,
+                'algorithmic_bytes_per_launch_avg': tot_bytes / max(n_rec, 1), 'peak_source': peak_src,
                 'launches_timed': n_rec, 'avg_launch_us': 1000.0 * tot_ms / max(n_rec, 1),
                 'achieved_tflops': tot_flops / (tot_ms / 1000.0) / 1e12 if tot_ms > 0 else 0.0,
                 'share_of_step': tot_ms / ms_roof, 'pass_ms_per_step': ms_roof / args.steps,
