@@ -63,17 +63,15 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons during the timed region, sampled in-process through NVML (spawning nvidia-smi every
-    200 ms perturbs the measurement); falls back to one nvidia-smi query per second when pynvml is unavailable."""
+class ClockSampler:
+    """SM clock + throttle reasons sampled through NVML from the MAIN thread (before, twice during and after the timed
+    region). A background sampling thread (or spawning nvidia-smi) measurably slows a host-bound step."""
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.stop_flag, self.sm, self.reasons_seen, self.max_mhz = index, False, [], set(), None
+        self.index, self.sm, self.reasons_seen, self.max_mhz, self.nv = index, [], set(), None, None
         try:
             import pynvml
             pynvml.nvmlInit()
-            self.nv = pynvml
             phys = index
             vis = os.environ.get('CUDA_VISIBLE_DEVICES')
             if vis:
@@ -83,31 +81,28 @@ class ClockSampler(threading.Thread):
                     phys = index
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
         except Exception:
             self.nv = None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                if self.nv is not None:
-                    nv = self.nv
-                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                    for name, bit in (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40),
-                                      ('sw_power_cap', 0x4)):
-                        if r & bit:
-                            self.reasons_seen.add(name)
-                    time.sleep(0.25)     # NVML queries contend with the CUDA driver lock: keep them sparse
-                else:
-                    q = 'clocks.sm,clocks.max.sm'
-                    out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
-                                          '--format=csv,noheader,nounits'], capture_output=True, text=True,
-                                         timeout=5).stdout.strip().split(',')
-                    self.sm.append(float(out[0]))
-                    self.max_mhz = float(out[1])
-                    time.sleep(1.0)
-            except Exception:
-                time.sleep(0.2)
+    def sample(self):
+        try:
+            if self.nv is not None:
+                nv = self.nv
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40),
+                                  ('sw_power_cap', 0x4)):
+                    if r & bit:
+                        self.reasons_seen.add(name)
+            else:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', '--query-gpu=clocks.sm,clocks.max.sm',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                     timeout=5).stdout.strip().split(',')
+                self.sm.append(float(out[0]))
+                self.max_mhz = float(out[1])
+        except Exception:
+            pass
 
     def summary(self):
         if not self.sm:
@@ -281,7 +276,7 @@ def main():
     log('roofline pass done')
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    sample_at = {max(args.steps // 3, 0), max(2 * args.steps // 3, 0)}
     _ffi.launch_counter.update(kernels=0, calls=0, by_name={})
     prof_range = os.environ.get('ESB_CUDA_PROFILER_RANGE') == '1'    # for `ncu --profile-from-start off`
     if prof_range:
@@ -290,11 +285,12 @@ def main():
     e0.record()
     for j in range(args.steps):
         logs = step(args.warmup + j)
+        if j in sample_at:
+            sampler.sample()          # under load, inside the timed region
     e1.record()
     barrier()
     if prof_range:
         torch.cuda.profiler.stop()
-    sampler.stop_flag = True
     log('timed region done')
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:

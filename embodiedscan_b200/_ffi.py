@@ -35,7 +35,7 @@ SIGNATURES = {
     'esb_maxpool_bwd': ('pppqiip', 'i'),
     'esb_norm_fwd': ('ppppiqiippfppfipppip', 'i'),
     'esb_norm_apply': ('pppqippppipip', 'i'),
-    'esb_norm_bwd': ('pppppiqiipppippppip', 'i'),
+    'esb_norm_bwd': ('pppppiqiipppippppiip', 'i'),
     'esb_act_fwd': ('ppqiip', 'i'),
     'esb_bias_act_fwd': ('ppppqiiip', 'i'),
     'esb_act_bwd': ('pppqiip', 'i'),

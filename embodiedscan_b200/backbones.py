@@ -128,6 +128,23 @@ class _ConvBN(nn.Module):
         super().__init__()
         self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
         self.bn = nn.BatchNorm2d(cout)
+        self._fold_key, self._fold_cache, self._const_w = None, None, {}
+
+    def _folded_constants(self):
+        """scale = gamma / sqrt(var + eps) (C,1,1,1) and shift = beta - mean * scale (C,), cached while the frozen BN
+        tensors are unchanged (norm_eval + requires_grad=False: they never change during training)."""
+        bn = self.bn
+        key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               bn.weight.data_ptr(), bn.weight.device)
+        if self._fold_key != key or bn.weight.requires_grad or bn.bias.requires_grad:
+            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            shift = (bn.bias - bn.running_mean * scale).float()
+            if bn.weight.requires_grad or bn.bias.requires_grad:
+                return scale[:, None, None, None], shift          # trainable affine: keep the autograd graph, no cache
+            self._fold_cache = (scale.detach()[:, None, None, None].contiguous(), shift.detach().contiguous())
+            self._fold_key = key
+            self._const_w = {}
+        return self._fold_cache
 
     def forward(self, x, relu, res=None):
         if x.dtype == torch.float32 and x.is_cuda and torch.backends.cudnn.allow_tf32:
@@ -142,9 +159,13 @@ class _ConvBN(nn.Module):
             y = bn(F.conv2d(x, conv.weight.to(x.dtype), None, conv.stride, conv.padding))
             y = y + res if res is not None else y
             return F.relu(y, inplace=True) if relu else y
-        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-        w = (conv.weight * scale[:, None, None, None]).to(x.dtype)
-        b = (bn.bias - bn.running_mean * scale).float()
+        scale4, b = self._folded_constants()
+        if conv.weight.requires_grad:
+            w = (conv.weight * scale4).to(x.dtype)
+        else:                       # frozen stage: the folded bf16/fp32 kernel is a constant too
+            w = self._const_w.get(x.dtype)
+            if w is None:
+                w = self._const_w[x.dtype] = (conv.weight.detach() * scale4).to(x.dtype)
         y = F.conv2d(x, w, None, conv.stride, conv.padding)
         if y.is_cuda and y.shape[1] % 8 == 0 and y.is_contiguous(memory_format=torch.channels_last):
             return _BiasResAct.apply(y, b, res, SP.ACT_RELU if relu else SP.ACT_NONE)   # bias + residual + ReLU fused

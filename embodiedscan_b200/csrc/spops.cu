@@ -329,11 +329,14 @@ extern "C" int esb_norm_apply(const void* x, const void* res, const int* row_seg
 // Backward: dgamma = sgx summed over segments, dbeta = sg summed over segments (the host sums the (S,C) arrays).
 extern "C" int esb_norm_bwd(const void* x, const void* y, const void* dy, const int* seg_off, const int* row_seg, int S,
                             long long N, int max_seg_rows, int C, const float* mean, const float* rstd,
-                            const float* gamma, int act, float* sg, float* sgx, void* dx, void* dres, int dtype,
-                            void* stream_) {
+                            const float* gamma, int act, float* sg, float* sgx, void* dx, void* dres, int zero_sums,
+                            int dtype, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  ESB_CUDA_CALL(cudaMemsetAsync(sg, 0, sizeof(float) * S * C, stream));
-  ESB_CUDA_CALL(cudaMemsetAsync(sgx, 0, sizeof(float) * S * C, stream));
+  // zero_sums = 0: sg/sgx are the (already zeroed, used once per step) gradient slots of beta/gamma in the flat arena
+  if (zero_sums) {
+    ESB_CUDA_CALL(cudaMemsetAsync(sg, 0, sizeof(float) * S * C, stream));
+    ESB_CUDA_CALL(cudaMemsetAsync(sgx, 0, sizeof(float) * S * C, stream));
+  }
   if (N == 0) return ESB_OK;
   const int rpb = 256;
   dim3 grid(esb_div_up(max_seg_rows > 0 ? max_seg_rows : 1, rpb), S, esb_div_up(C, 32)), block(32, 8);

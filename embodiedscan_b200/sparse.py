@@ -352,6 +352,7 @@ class _SegNorm(torch.autograd.Function):
         ctx.save_for_backward(x, y, mean, rstd, g, seg_off, row_seg)   # None entries are allowed
         ctx.meta = (S, max_rows, act, res is not None, gamma.shape if gamma is not None else None,
                     beta.shape if beta is not None else None)
+        ctx.params = (gamma, beta)
         return y
 
     @staticmethod
@@ -360,12 +361,23 @@ class _SegNorm(torch.autograd.Function):
         S, max_rows, act, has_res, gshape, bshape = ctx.meta
         N, C = x.shape
         dy = dy.contiguous()
-        sg = torch.empty((S, C), dtype=torch.float32, device=x.device)
-        sgx = torch.empty((S, C), dtype=torch.float32, device=x.device)
+        gamma, beta = ctx.params
+        direct = (S == 1 and gamma is not None and beta is not None and getattr(gamma, '_esb_grad_direct', False)
+                  and getattr(beta, '_esb_grad_direct', False) and gamma.grad is not None and beta.grad is not None)
+        if direct:   # the column sums ARE d(beta), d(gamma): accumulate them in the arena's (zeroed) gradient slots
+            sg, sgx = beta.grad, gamma.grad
+        else:
+            sg = torch.empty((S, C), dtype=torch.float32, device=x.device)
+            sgx = torch.empty((S, C), dtype=torch.float32, device=x.device)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
         call('esb_norm_bwd', ptr(x), ptr(y), ptr(dy), ptr(seg_off), ptr(row_seg), S, N, max_rows, C, ptr(mean), ptr(rstd),
-             ptr(g), act, ptr(sg), ptr(sgx), ptr(dx), ptr(dres), _ffi.dtype_code(x.dtype), stream())
+             ptr(g), act, ptr(sg), ptr(sgx), ptr(dx), ptr(dres), 0 if direct else 1, _ffi.dtype_code(x.dtype), stream())
+        if direct:
+            for prm in (gamma, beta):
+                for hook in (getattr(prm, '_post_accumulate_grad_hooks', None) or {}).values():
+                    hook(prm)
+            return dx, dres, None, None, None, None, None, None, None, None, None, None, None
         if S == 1:       # BatchNorm: the (1,C) sums ARE the parameter gradients (no reduction kernel)
             dgamma = sgx.view(gshape) if gshape is not None else None
             dbeta = sg.view(bshape) if bshape is not None else None

@@ -79,7 +79,7 @@ int esb_norm_apply(const void* x, const void* res, const int* row_seg, long long
                    const float* rstd, const float* gamma, const float* beta, int act, void* y, int dtype, void* stream);
 int esb_norm_bwd(const void* x, const void* y, const void* dy, const int* seg_off, const int* row_seg, int S,
                  long long N, int max_seg_rows, int C, const float* mean, const float* rstd, const float* gamma, int act,
-                 float* sg, float* sgx, void* dx, void* dres, int dtype, void* stream);
+                 float* sg, float* sgx, void* dx, void* dres, int zero_sums, int dtype, void* stream);
 int esb_act_fwd(const void* x, void* y, long long n, int act, int dtype, void* stream);
 /* fused epilogue of the folded conv+BN blocks of the per-view 2D ResNet: y = act(x + bias[c] + res) on NHWC rows */
 int esb_bias_act_fwd(const void* x, const float* bias, const void* res, void* y, long long rows, int C, int act,
