@@ -49,6 +49,7 @@ SIGNATURES = {
     'esb_bbox_cd_loss': ('pppppippp', 'i'),
     'esb_nms_bev_segmented': ('ppiifipp', 'i'),
     'esb_iou_bev_pairwise': ('pipiipp', 'i'),
+    'esb_box3d_overlap': ('pipippp', 'i'),
     'esb_img_normalize': ('piiiiippiipip', 'i'),
     'esb_unproject_depth_workspace_bytes': ('iii', 'z'),
     'esb_unproject_depth': ('piiifpppppzp', 'i'),

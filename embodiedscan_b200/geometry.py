@@ -92,3 +92,16 @@ def chamfer_l1_src(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
 def bbox_cd_loss(source: torch.Tensor, target: torch.Tensor, loss_weight: float = 1.0) -> torch.Tensor:
     """BBoxCDLoss(mode='l1', group='g8', reduction='mean') (chamfer_distance.py:240-285)."""
     return chamfer_l1_src(bbox_to_corners(source), bbox_to_corners(target)).mean() * loss_weight
+
+
+def box3d_overlap(corners1: torch.Tensor, corners2: torch.Tensor, eps: float = 1e-4):
+    """pytorch3d.ops.box3d_overlap contract: corners (N,8,3), (M,8,3) in the container's corner order -> (vol, iou),
+    both (N,M). Exact convex clipping on the GPU (csrc/iou3d.cu); `eps` is accepted for signature parity."""
+    from ._ffi import call, ptr, stream
+    assert corners1.is_cuda, 'box3d_overlap runs in libesb200.so (no CPU fallback)'
+    c1, c2 = corners1.float().contiguous(), corners2.float().contiguous()
+    n1, n2 = c1.shape[0], c2.shape[0]
+    vol = torch.empty((n1, n2), dtype=torch.float32, device=c1.device)
+    iou = torch.empty((n1, n2), dtype=torch.float32, device=c1.device)
+    call('esb_box3d_overlap', ptr(c1), n1, ptr(c2), n2, ptr(vol), ptr(iou), stream())
+    return vol, iou

@@ -122,6 +122,15 @@ class EulerDepthInstance3DBoxes:
         out = EulerDepthInstance3DBoxes(self.tensor.to(device), box_dim=9, with_yaw=self.with_yaw)
         return out
 
+    @classmethod
+    def overlaps(cls, boxes1, boxes2, mode='iou', eps=1e-4):
+        """(N,M) 9-DoF 3D IoU (euler_box3d.py:103-135)."""
+        from .geometry import box3d_overlap
+        assert mode == 'iou'
+        if len(boxes1) * len(boxes2) == 0:
+            return boxes1.tensor.new_zeros((len(boxes1), len(boxes2)))
+        return box3d_overlap(boxes1.corners, boxes2.corners, eps=eps)[1]
+
     def __getitem__(self, item):
         t = self.tensor[item]
         if t.dim() == 1:

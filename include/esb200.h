@@ -118,6 +118,10 @@ int esb_nms_bev_segmented(const float* boxes, const int* seg_off, int S, int max
                           unsigned char* keep, void* stream);
 int esb_iou_bev_pairwise(const float* a, int na, const float* b, int nb, int rotated, float* out, void* stream);
 
+/* ---- exact 9-DoF box IoU (pytorch3d.ops.box3d_overlap via EulerInstance3DBoxes.overlaps, euler_box3d.py:103-135) ---- */
+int esb_box3d_overlap(const float* corners1, int n1, const float* corners2, int n2, float* vol, float* iou,
+                      void* stream);
+
 /* ---- input side: Det3DDataPreprocessor image path (data_preprocessor.py:249-264, utils.py:9-63) and the
  * depth->points unprojection (datasets/transforms/points.py:30-81, multiview.py:139-169) ------------------------- */
 int esb_img_normalize(const unsigned char* src, int n_img, int H, int W, int Hp, int Wp, const float* mean3_host,

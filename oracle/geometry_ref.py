@@ -212,3 +212,66 @@ def multiclass_nms(bboxes: torch.Tensor, scores: torch.Tensor, score_thr: float,
         return torch.zeros((0, 7)), torch.zeros((0, )), torch.zeros((0, ), dtype=torch.long)
     return (torch.from_numpy(np.concatenate(out_b)), torch.from_numpy(np.concatenate(out_s)),
             torch.from_numpy(np.concatenate(out_l)))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# exact 9-DoF box IoU (pytorch3d.ops.box3d_overlap contract, †upstream), float64 polygon clipping
+# ---------------------------------------------------------------------------------------------------------
+def _box_from_corners(k):
+    c = k.mean(0)
+    e = [k[4] - k[0], k[3] - k[0], k[1] - k[0]]
+    h = [np.linalg.norm(v) / 2 for v in e]
+    n = [v / (2 * hh) for v, hh in zip(e, h)]
+    return c, n, h
+
+
+def _clip(poly, n, d, strict):
+    out = []
+    for i in range(len(poly)):
+        a, b = poly[i], poly[(i + 1) % len(poly)]
+        da, db = n @ a - d, n @ b - d
+        ina, inb = (da < -1e-12, db < -1e-12) if strict else (da <= 1e-12, db <= 1e-12)
+        if ina:
+            out.append(a)
+        if ina != inb:
+            out.append(a + (b - a) * (da / (da - db)))
+    return out
+
+
+def _faces_clipped(P, Q, strict):
+    (pc, pn, ph), (qc, qn, qh) = P, Q
+    acc = 0.0
+    for a in range(3):
+        for sgn in (-1.0, 1.0):
+            n = pn[a] * sgn
+            fc = pc + n * ph[a]
+            u, v = pn[(a + 1) % 3] * ph[(a + 1) % 3], pn[(a + 2) % 3] * ph[(a + 2) % 3]
+            poly = [fc - u - v, fc + u - v, fc + u + v, fc - u + v]
+            for b in range(3):
+                for s2 in (-1.0, 1.0):
+                    if poly:
+                        m = qn[b] * s2
+                        poly = _clip(poly, m, m @ qc + qh[b], strict)
+            if len(poly) < 3:
+                continue
+            av = sum((np.cross(poly[i] - poly[0], poly[i + 1] - poly[0]) for i in range(1, len(poly) - 1)), np.zeros(3))
+            acc += (n @ fc) * 0.5 * abs(av @ n)
+    return acc
+
+
+def box3d_overlap(corners1: np.ndarray, corners2: np.ndarray):
+    """(N,8,3),(M,8,3) in EulerInstance3DBoxes.corners order -> (vol, iou) float64. Faces of A∩B = faces of A clipped by B
+    plus faces of B strictly clipped by A; V = 1/3 sum (n.p) area (divergence theorem), relative to A's centre."""
+    n1, n2 = len(corners1), len(corners2)
+    vol, iou = np.zeros((n1, n2)), np.zeros((n1, n2))
+    for i in range(n1):
+        o = corners1[i].astype(np.float64).mean(0)
+        A = _box_from_corners(corners1[i].astype(np.float64) - o)
+        va = 8 * A[2][0] * A[2][1] * A[2][2]
+        for j in range(n2):
+            B = _box_from_corners(corners2[j].astype(np.float64) - o)
+            vb = 8 * B[2][0] * B[2][1] * B[2][2]
+            v = (_faces_clipped(A, B, False) + _faces_clipped(B, A, True)) / 3.0
+            v = min(max(v, 0.0), min(va, vb))
+            vol[i, j], iou[i, j] = v, v / max(va + vb - v, 1e-12)
+    return vol, iou

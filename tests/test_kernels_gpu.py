@@ -405,6 +405,29 @@ def test_multiclass_nms_selection_order(seed):
     assert rl.numel() > 30
 
 
+def test_box3d_overlap_9dof():
+    from embodiedscan_b200.structures import EulerDepthInstance3DBoxes
+    from oracle import geometry_ref as G
+    g = np.random.RandomState(3)
+
+    def boxes(n, spread):
+        b = np.zeros((n, 9), dtype=np.float32)
+        b[:, :3] = g.uniform(-spread, spread, (n, 3))
+        b[:, 3:6] = g.uniform(0.3, 1.6, (n, 3))
+        b[:, 6] = g.uniform(-math.pi, math.pi, n)
+        b[:, 7:] = g.normal(0, 0.4, (n, 2))
+        return torch.from_numpy(b)
+    b1, b2 = boxes(24, 0.8), boxes(18, 0.8)
+    b2[0] = b1[0]                                                   # identical pair: IoU 1 despite coplanar faces
+    b2[1] = torch.tensor([50., 50., 50., 1., 1., 1., 0., 0., 0.])   # far away: IoU 0
+    ref_vol, ref_iou = G.box3d_overlap(G.container_corners(b1).numpy(), G.container_corners(b2).numpy())
+    iou = EulerDepthInstance3DBoxes.overlaps(EulerDepthInstance3DBoxes(b1).to(_dev()), EulerDepthInstance3DBoxes(b2).to(_dev()))
+    assert iou.shape == (24, 18)
+    assert float((iou.cpu().double() - torch.from_numpy(ref_iou)).abs().max()) < 1e-4
+    assert abs(float(iou[0, 0]) - 1.0) < 1e-4 and float(iou[:, 1].max()) == 0.0
+    assert float((ref_iou > 0.05).mean()) > 0.2, 'the test must exercise real overlaps'
+
+
 # ------------------------------------------------------------------------------------------------ input side
 def test_img_normalize_bit_exact():
     from embodiedscan_b200 import Det3DDataPreprocessor

@@ -138,3 +138,33 @@ def test_oracle_detector_runs_c1():
     with torch.no_grad():
         losses = M.detector_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
     assert all(torch.isfinite(v) for v in losses.values()) and float(losses['loss_cls']) > 0
+
+
+def test_box3d_overlap_closed_forms_and_monte_carlo():
+    def corners(b):
+        return G.container_corners(torch.tensor([b], dtype=torch.float32))[0].numpy()
+    a = corners([0, 0, 0, 2, 2, 2, 0, 0, 0])
+    vol, iou = G.box3d_overlap(a[None], a[None])
+    assert abs(vol[0, 0] - 8) < 1e-9 and abs(iou[0, 0] - 1) < 1e-9                      # identical (coplanar faces)
+    b = corners([1, 0.5, 0, 2, 2, 2, 0, 0, 0])
+    vol, iou = G.box3d_overlap(a[None], b[None])
+    assert abs(vol[0, 0] - 1 * 1.5 * 2) < 1e-9 and abs(iou[0, 0] - 3 / 13) < 1e-9       # axis-aligned shift
+    c = corners([0, 0, 0.5, 2, 2, 2, math.pi / 4, 0, 0])
+    vol, _ = G.box3d_overlap(a[None], c[None])
+    assert abs(vol[0, 0] - 8 * (math.sqrt(2) - 1) * 1.5) < 1e-6                         # octagonal prism, height 1.5
+    d = corners([0.1, -0.2, 0.1, 0.5, 0.4, 0.3, 0.3, 0.2, -0.4])
+    vol, _ = G.box3d_overlap(a[None], d[None])
+    assert abs(vol[0, 0] - 0.5 * 0.4 * 0.3) < 1e-6                                      # contained box (fp32 corners)
+    far = corners([9, 9, 9, 1, 1, 1, 0.3, 0.1, 0.2])
+    assert G.box3d_overlap(a[None], far[None])[0][0, 0] == 0
+    # Monte-Carlo volume of a generic 9-DoF pair
+    b1 = torch.tensor([[0.1, 0.0, 0.2, 1.5, 1.0, 0.8, 0.7, 0.2, -0.3]])
+    b2 = torch.tensor([[0.4, 0.3, 0.1, 1.2, 1.4, 0.9, -0.5, 0.4, 0.25]])
+    vol, _ = G.box3d_overlap(G.container_corners(b1).numpy(), G.container_corners(b2).numpy())
+    g = torch.Generator().manual_seed(0)
+    pts = (torch.rand(400000, 3, generator=g) - 0.5) * b1[0, 3:6]                       # uniform in box 1's frame
+    world = pts @ G.euler_to_matrix(b1[:, 6:9])[0].T + b1[0, :3]
+    local2 = (world - b2[0, :3]) @ G.euler_to_matrix(b2[:, 6:9])[0]
+    inside = (local2.abs() <= b2[0, 3:6] / 2).all(1).float().mean()
+    mc = float(inside) * float(b1[0, 3:6].prod())
+    assert abs(vol[0, 0] - mc) < 0.01 * float(b1[0, 3:6].prod())
