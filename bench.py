@@ -306,11 +306,11 @@ def main():
     n_rec = 0
     wg_bytes = wg_ms = 0.0
     pair_cache = {}
-    for kind, kmap, cin, cout, _dt, a, b in SP.CONV_PROFILE['records']:
-        if id(kmap) not in pair_cache:
-            pair_cache[id(kmap)] = int(kmap.pairs[2][-1].item())
-        P = pair_cache[id(kmap)]
-        by = P * (cin + cout) * e + 8 * P + kmap.K * cin * cout * e
+    for kind, koff, K_, cin, cout, _dt, a, b in SP.CONV_PROFILE['records']:
+        if id(koff) not in pair_cache:
+            pair_cache[id(koff)] = int(koff[-1].item())
+        P = pair_cache[id(koff)]
+        by = P * (cin + cout) * e + 8 * P + K_ * cin * cout * e
         t = a.elapsed_time(b)
         if kind == 'wgrad':
             wg_bytes += by

@@ -39,7 +39,8 @@ def _timed_conv_call(kind, kmap, cin, cout, dtype, *args):
     e0.record()
     call(*args)
     e1.record()
-    CONV_PROFILE['records'].append((kind, kmap, cin, cout, dtype, e0, e1))
+    # keep only the tiny (K+1) pair-offset tensor: holding the KernelMap would pin hundreds of MB of maps per step
+    CONV_PROFILE['records'].append((kind, kmap.pairs[2], kmap.K, cin, cout, dtype, e0, e1))
 
 
 def _offsets(kernel_size: int, scale: int) -> List[int]:

@@ -131,15 +131,20 @@ def test_arena_direct_gradients_equal_autograd(dtype):
     for m in (plain, arena_model):
         data = m.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
         sum(m(**data, mode='loss').values()).backward()
-    worst = 0.
+    num = den = 0.
     for (n1, p1), (n2, p2) in zip(plain.named_parameters(), arena_model.named_parameters()):
         assert n1 == n2
         if p1.grad is None:
             assert not p2.requires_grad or float(p2.grad.abs().sum()) == 0.
             continue
-        scale = max(float(p1.grad.abs().max()), 1e-8)
-        err = float((p1.grad - p2.grad).abs().max()) / scale
-        worst = max(worst, err)
-        # (2D-backbone gradients pass through fp32 atomics in paint-bwd and cuDNN wgrad: run-to-run noise ~3e-4)
-        assert err <= (2e-3 if dtype == torch.float32 else 2e-2), (n1, err)
-    assert worst >= 0.
+        diff, ref = float((p1.grad - p2.grad).norm()), float(p1.grad.norm())
+        num, den = num + diff ** 2, den + ref ** 2
+        if dtype == torch.float32:
+            # (2D-backbone gradients pass through fp32 atomics in paint-bwd and cuDNN wgrad: run-to-run noise ~3e-4)
+            scale = max(float(p1.grad.abs().max()), 1e-8)
+            assert float((p1.grad - p2.grad).abs().max()) / scale <= 2e-3, n1
+        else:
+            # bf16: atomic-order noise is re-rounded to 8 mantissa bits layer after layer; a stale or misaligned bf16
+            # shadow arena would give O(1) errors
+            assert diff <= 0.25 * ref + 1e-6, (n1, diff, ref)
+    assert (num / max(den, 1e-30)) ** 0.5 <= (1e-3 if dtype == torch.float32 else 5e-2)
