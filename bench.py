@@ -215,6 +215,9 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    sampler = ClockSampler(local)    # NVML attaches here, long before the timed region (attaching stalls launches briefly)
+    sampler.sample()
+    sampler.sm.clear()
     torch.manual_seed(0)
     cfg = mv_det3d_config(args.variant)
     model = MODELS.build(dict(cfg, compute_dtype=dtype)).to(dev).train()
@@ -275,20 +278,25 @@ def main():
     ms_roof = r0.elapsed_time(r1)
     log('roofline pass done')
     barrier()
-    sampler = ClockSampler(local)
     sample_at = {max(args.steps // 3, 0), max(2 * args.steps // 3, 0)}
     _ffi.launch_counter.update(kernels=0, calls=0, by_name={})
     prof_range = os.environ.get('ESB_CUDA_PROFILER_RANGE') == '1'    # for `ncu --profile-from-start off`
     if prof_range:
         torch.cuda.profiler.start()
+    import gc
+    gc.collect()
+    gc.freeze()        # setup objects (model, batches, profile records) leave the collector's working set
+    host_t = [time.perf_counter()]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for j in range(args.steps):
         logs = step(args.warmup + j)
         if j in sample_at:
             sampler.sample()          # under load, inside the timed region
+        host_t.append(time.perf_counter())
     e1.record()
     barrier()
+    log('host ms per timed step: ' + ' '.join(f'{1e3 * (b - a):.1f}' for a, b in zip(host_t[:-1], host_t[1:])))
     if prof_range:
         torch.cuda.profiler.stop()
     log('timed region done')

@@ -230,6 +230,8 @@ __global__ void assign_kernel(const float* __restrict__ pts, const int* __restri
 
 // ---------------- sigmoid focal loss (mmcv CUDA semantics) ----------------
 __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+// x^gamma with the configured gamma = 2 as a multiply (general powf is ~20x the cost of the rest of the element)
+__device__ __forceinline__ float pow_gamma(float x, float gamma) { return gamma == 2.f ? x * x : powf(x, gamma); }
 
 template <typename T>
 __global__ void focal_fwd_kernel(const T* __restrict__ logits, const long long* __restrict__ target, long long n, int C,
@@ -241,9 +243,9 @@ __global__ void focal_fwd_kernel(const T* __restrict__ logits, const long long* 
     int c = (int)(t - r * C);
     float p = sigmoidf(esb_to_float<T>(logits[t]));
     if (target[r] == c)
-      l = -alpha * powf(1.f - p, gamma) * logf(fmaxf(p, 1.17549435e-38f));
+      l = -alpha * pow_gamma(1.f - p, gamma) * logf(fmaxf(p, 1.17549435e-38f));
     else
-      l = -(1.f - alpha) * powf(p, gamma) * logf(fmaxf(1.f - p, 1.17549435e-38f));
+      l = -(1.f - alpha) * pow_gamma(p, gamma) * logf(fmaxf(1.f - p, 1.17549435e-38f));
     if (row_w) l *= row_w[r];
   }
   l = esb_warp_sum(l);
@@ -269,9 +271,9 @@ __global__ void focal_bwd_kernel(const T* __restrict__ logits, const long long* 
   float p = sigmoidf(esb_to_float<T>(logits[t]));
   float g;
   if (target[r] == c)
-    g = -alpha * powf(1.f - p, gamma) * (1.f - p - gamma * p * logf(fmaxf(p, 1.17549435e-38f)));
+    g = -alpha * pow_gamma(1.f - p, gamma) * (1.f - p - gamma * p * logf(fmaxf(p, 1.17549435e-38f)));
   else
-    g = -(1.f - alpha) * powf(p, gamma) * (gamma * (1.f - p) * logf(fmaxf(1.f - p, 1.17549435e-38f)) - p);
+    g = -(1.f - alpha) * pow_gamma(p, gamma) * (gamma * (1.f - p) * logf(fmaxf(1.f - p, 1.17549435e-38f)) - p);
   grad[t] = esb_from_float<T>(g * scale[0] * (row_w ? row_w[r] : 1.f));
 }
 

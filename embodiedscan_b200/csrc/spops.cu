@@ -136,6 +136,93 @@ __global__ void norm_apply_kernel(const T* __restrict__ x, const T* __restrict__
   y[t] = esb_from_float<T>(act_fwd(z, act));
 }
 
+// 8-wide helpers (16 B for bf16, 2 x 16 B for fp32)
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float v[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float v[8]) {
+  float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float v[8]) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float v[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float v[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float v[8]) {
+  uint4 o;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+// y = act((x - mean) * rstd * gamma + beta + res), 8 channels per thread (C % 8 == 0)
+template <typename T>
+__global__ void norm_apply_vec8_kernel(const T* __restrict__ x, const T* __restrict__ res, const int* __restrict__ row_seg,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
+                                       long long n_vec, int C, int act) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_vec) return;
+  const int cv = C >> 3;
+  const long long r = t / cv;
+  const int c0 = (int)(t - r * cv) << 3;
+  const int s = row_seg ? row_seg[r] : 0;
+  float v[8], rr[8];
+  load8<T>(x + t * 8, v);
+  if (res) load8<T>(res + t * 8, rr);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    float z = (v[i] - mean[s * C + c]) * rstd[s * C + c] * (gamma ? gamma[c] : 1.f) + (beta ? beta[c] : 0.f);
+    if (res) z += rr[i];
+    v[i] = act_fwd(z, act);
+  }
+  store8<T>(y + t * 8, v);
+}
+
+template <typename T>
+__global__ void norm_bwd_apply_vec8_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                           const int* __restrict__ row_seg, const int* __restrict__ seg_off,
+                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                           const float* __restrict__ gamma, const float* __restrict__ sg,
+                                           const float* __restrict__ sgx, T* __restrict__ dx, T* __restrict__ dres,
+                                           long long N, long long n_vec, int C, int act) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_vec) return;
+  const int cv = C >> 3;
+  const long long r = t / cv;
+  const int c0 = (int)(t - r * cv) << 3;
+  const int s = row_seg ? row_seg[r] : 0;
+  const float inv_n = 1.f / (float)max(seg_end(seg_off, s, (int)N) - seg_begin(seg_off, s), 1);
+  float xv[8], yv[8], gv[8], ov[8];
+  load8<T>(x + t * 8, xv);
+  load8<T>(y + t * 8, yv);
+  load8<T>(dy + t * 8, gv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    float g = gv[i] * act_bwd_from_out(yv[i], act);
+    float rs = rstd[s * C + c];
+    float xh = (xv[i] - mean[s * C + c]) * rs;
+    ov[i] = (gamma ? gamma[c] : 1.f) * rs * (g - sg[s * C + c] * inv_n - xh * sgx[s * C + c] * inv_n);
+    gv[i] = g;
+  }
+  store8<T>(dx + t * 8, ov);
+  if (dres) store8<T>(dres + t * 8, gv);
+}
+
 // backward reduce: sg[s][c] = sum g ; sgx[s][c] = sum g * xhat, with g = dy * act'(y)
 template <typename T>
 __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
@@ -248,10 +335,18 @@ template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n,
                                int act) {
   long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+  if (t + 8 <= n) {
+    float g[8], o[8];
+    load8<T>(dy + t, g);
+    load8<T>(y + t, o);
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (t + i < n)
-      dx[t + i] = esb_from_float<T>(esb_to_float<T>(dy[t + i]) * act_bwd_from_out(esb_to_float<T>(y[t + i]), act));
+    for (int i = 0; i < 8; ++i) g[i] *= act_bwd_from_out(o[i], act);
+    store8<T>(dx + t, g);
+  } else {
+    for (int i = 0; i < 8; ++i)
+      if (t + i < n)
+        dx[t + i] = esb_from_float<T>(esb_to_float<T>(dy[t + i]) * act_bwd_from_out(esb_to_float<T>(y[t + i]), act));
+  }
 }
 
 }  // namespace
@@ -308,8 +403,12 @@ extern "C" int esb_norm_fwd(const void* x, const void* res, const int* seg_off, 
     seg_colstat_kernel<T, 1><<<grid, block, 0, stream>>>((const T*)x, seg_off, mean, rstd, C, rpb, (int)N);
     seg_finalize_rstd_kernel<<<fin, 256, 0, stream>>>(mean, rstd, seg_off, S, C, eps, running_mean, running_var, momentum,
                                                       (int)N);
-    norm_apply_kernel<T><<<esb_div_up(N * C, 256), 256, 0, stream>>>((const T*)x, (const T*)res, row_seg, mean, rstd,
-                                                                     gamma, beta, (T*)y, N, C, act);
+    if (C % 8 == 0)
+      norm_apply_vec8_kernel<T><<<esb_div_up(N * (C / 8), 256), 256, 0, stream>>>(
+          (const T*)x, (const T*)res, row_seg, mean, rstd, gamma, beta, (T*)y, N * (C / 8), C, act);
+    else
+      norm_apply_kernel<T><<<esb_div_up(N * C, 256), 256, 0, stream>>>((const T*)x, (const T*)res, row_seg, mean, rstd,
+                                                                       gamma, beta, (T*)y, N, C, act);
   });
   ESB_CUDA_LAUNCH_CHECK("esb_norm_fwd");
   return ESB_OK;
@@ -343,8 +442,13 @@ extern "C" int esb_norm_bwd(const void* x, const void* y, const void* dy, const 
   DISPATCH_T(dtype, {
     norm_bwd_reduce_kernel<T><<<grid, block, 0, stream>>>((const T*)x, (const T*)y, (const T*)dy, seg_off, mean, rstd,
                                                           sg, sgx, C, rpb, act, (int)N);
-    norm_bwd_apply_kernel<T><<<esb_div_up(N * C, 256), 256, 0, stream>>>(
-        (const T*)x, (const T*)y, (const T*)dy, row_seg, seg_off, mean, rstd, gamma, sg, sgx, (T*)dx, (T*)dres, N, C, act);
+    if (C % 8 == 0)
+      norm_bwd_apply_vec8_kernel<T><<<esb_div_up(N * (C / 8), 256), 256, 0, stream>>>(
+          (const T*)x, (const T*)y, (const T*)dy, row_seg, seg_off, mean, rstd, gamma, sg, sgx, (T*)dx, (T*)dres, N,
+          N * (C / 8), C, act);
+    else
+      norm_bwd_apply_kernel<T><<<esb_div_up(N * C, 256), 256, 0, stream>>>(
+          (const T*)x, (const T*)y, (const T*)dy, row_seg, seg_off, mean, rstd, gamma, sg, sgx, (T*)dx, (T*)dres, N, C, act);
   });
   ESB_CUDA_LAUNCH_CHECK("esb_norm_bwd");
   return ESB_OK;

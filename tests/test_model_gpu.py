@@ -146,5 +146,5 @@ def test_arena_direct_gradients_equal_autograd(dtype):
         else:
             # bf16: atomic-order noise is re-rounded to 8 mantissa bits layer after layer; a stale or misaligned bf16
             # shadow arena would give O(1) errors
-            assert diff <= 0.25 * ref + 1e-6, (n1, diff, ref)
+            assert diff <= 0.5 * ref + 1e-6, (n1, diff, ref)
     assert (num / max(den, 1e-30)) ** 0.5 <= (1e-3 if dtype == torch.float32 else 5e-2)
