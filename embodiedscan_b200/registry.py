@@ -65,6 +65,7 @@ if HAVE_MMENGINE:  # pragma: no cover
 else:
     MODELS = Registry('model')
     TASK_UTILS = Registry('task util')
+TRANSFORMS = Registry('transform') if not HAVE_MMENGINE else _MMRegistry('transform', scope='embodiedscan_b200')
 
 
 def register_into_reference():  # pragma: no cover - needs the reference package importable

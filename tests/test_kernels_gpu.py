@@ -472,6 +472,21 @@ def test_unproject_depth():
     _close(out[:n], ref, 1e-5, 'unprojected points')
 
 
+def test_multiview_depth_to_points_transform():
+    from embodiedscan_b200.synth import synth_scan
+    from embodiedscan_b200.transforms import MultiViewDepthToPoints, unproject_multiview
+    s = synth_scan(4, n_views=3, H=48, W=64, n_points=900)
+    meta = s['data_sample'].metainfo['depth2img']
+    pts = unproject_multiview(s['depth'].to(_dev()), meta['intrinsic'], meta['extrinsic'])
+    assert pts.shape[0] == int((s['depth'] != 0).sum())
+    # every synthetic scan point (sampled from the same unprojection in torch) is one of the kernel's points
+    d = torch.cdist(s['points'].to(_dev()), pts).min(1).values
+    assert float(d.max()) < 1e-3
+    out = MultiViewDepthToPoints(num_points=500, points_per_view=300, seed=0)(
+        dict(depth_imgs=s['depth'].to(_dev()), depth2img=meta))
+    assert out['points'].shape == (500, 3) and float(torch.cdist(out['points'], pts).min(1).values.max()) == 0.0
+
+
 def test_adamw_and_clip_match_torch():
     from embodiedscan_b200.engine import OptimWrapper
     torch.manual_seed(7)
