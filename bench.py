@@ -286,6 +286,9 @@ def main():
     import gc
     gc.collect()
     gc.freeze()        # setup objects (model, batches, profile records) leave the collector's working set
+    for j in range(3):             # pre-roll: after an idle period (barrier, gc, logging) the device runs slow for
+        step(j)                    # ~0.2 s and the backlog surfaces at the next host sync; drain it before timing
+    torch.cuda.synchronize()
     host_t = [time.perf_counter()]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

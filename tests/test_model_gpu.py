@@ -116,35 +116,45 @@ def test_train_steps_reduce_loss():
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_arena_direct_gradients_equal_autograd(dtype):
     """engine.FlatArena lets the wgrad / BatchNorm-backward kernels accumulate straight into the flat gradient buffer
-    (and, in bf16, feeds them the arena's bf16 shadow weights): every gradient must equal the plain autograd path."""
+    (and, in bf16, feeds them the arena's bf16 shadow weights): every gradient must equal the plain autograd path.
+    fp32: tight bound. bf16: atomic-order noise is re-rounded to 8 mantissa bits layer after layer, so the bound is the
+    run-to-run difference of two PLAIN models (measured in the same test) times a small factor."""
     from embodiedscan_b200 import MODELS
     from embodiedscan_b200.engine import FlatArena
     from embodiedscan_b200.synth import mv_det3d_config, synth_batch
     torch.manual_seed(0)
     cfg = dict(mv_det3d_config('C2' if dtype == torch.bfloat16 else 'C1'), compute_dtype=dtype)
-    plain = MODELS.build(cfg).to(DEV).train()
-    arena_model = MODELS.build(cfg).to(DEV).train()
-    arena_model.load_state_dict(plain.state_dict())
-    arena = FlatArena(arena_model)
+    models = [MODELS.build(cfg).to(DEV).train() for _ in range(3)]
+    for m in models[1:]:
+        m.load_state_dict(models[0].state_dict())
+    arena = FlatArena(models[2])
     arena.zero_grad()
     batch = synth_batch(1, 2, n_views=2, H=240, W=320, n_points=2000, augment=True)
-    for m in (plain, arena_model):
+    losses = []
+    for m in models:
         data = m.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
-        sum(m(**data, mode='loss').values()).backward()
-    num = den = 0.
-    for (n1, p1), (n2, p2) in zip(plain.named_parameters(), arena_model.named_parameters()):
-        assert n1 == n2
-        if p1.grad is None:
-            assert not p2.requires_grad or float(p2.grad.abs().sum()) == 0.
-            continue
-        diff, ref = float((p1.grad - p2.grad).norm()), float(p1.grad.norm())
-        num, den = num + diff ** 2, den + ref ** 2
-        if dtype == torch.float32:
-            # (2D-backbone gradients pass through fp32 atomics in paint-bwd and cuDNN wgrad: run-to-run noise ~3e-4)
-            scale = max(float(p1.grad.abs().max()), 1e-8)
-            assert float((p1.grad - p2.grad).abs().max()) / scale <= 2e-3, n1
-        else:
-            # bf16: atomic-order noise is re-rounded to 8 mantissa bits layer after layer; a stale or misaligned bf16
-            # shadow arena would give O(1) errors
-            assert diff <= 0.5 * ref + 1e-6, (n1, diff, ref)
-    assert (num / max(den, 1e-30)) ** 0.5 <= (1e-3 if dtype == torch.float32 else 5e-2)
+        out = m(**data, mode='loss')
+        losses.append(float(sum(out.values()).detach()))
+        sum(out.values()).backward()
+    assert abs(losses[2] - losses[0]) <= (1e-5 if dtype == torch.float32 else 2e-2) * abs(losses[0])
+
+    def rel_err(ma, mb, check=None):
+        num = den = 0.
+        for (n1, p1), (n2, p2) in zip(ma.named_parameters(), mb.named_parameters()):
+            if p1.grad is None:
+                assert not p2.requires_grad or p2.grad is None or float(p2.grad.abs().sum()) == 0.
+                continue
+            num += float((p1.grad - p2.grad).norm()) ** 2
+            den += float(p1.grad.norm()) ** 2
+            if check is not None:
+                scale = max(float(p1.grad.abs().max()), 1e-8)
+                assert float((p1.grad - p2.grad).abs().max()) / scale <= check, n1
+        return (num / max(den, 1e-30)) ** 0.5
+
+    if dtype == torch.float32:
+        # (2D-backbone gradients pass through fp32 atomics in paint-bwd and cuDNN wgrad: run-to-run noise ~3e-4)
+        assert rel_err(models[0], models[2], check=2e-3) <= 1e-3
+    else:
+        noise = rel_err(models[0], models[1])
+        err = rel_err(models[0], models[2])
+        assert err <= 3.0 * noise + 2e-2, (err, noise)
