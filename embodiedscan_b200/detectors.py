@@ -104,6 +104,8 @@ class SparseFeatureFusionSingleStage3DDetector(nn.Module):
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
         self.voxel_size = bbox_head['voxel_size']
         self.use_xyz_feat = use_xyz_feat
+        self.overlap_2d_3d = True
+        self._side_stream = None
 
     # ---- feature extraction (sparse_featfusion_single_stage.py:86-221) --------------------------------------
     def voxelize(self, points: List[torch.Tensor]):
@@ -122,11 +124,6 @@ class SparseFeatureFusionSingleStage3DDetector(nn.Module):
 
     def extract_feat(self, batch_inputs_dict: Dict[str, torch.Tensor], batch_data_samples) -> List[SP.SparseTensor]:
         points = batch_inputs_dict['points']
-        coordinates, features = self.voxelize(points)
-        x = SP.SparseTensor(coordinates=coordinates, features=features.to(self.compute_dtype), batch_size=len(points))
-        x = self.backbone_3d(x)
-        num_levels = len(x)
-
         img = batch_inputs_dict['imgs']
         batch_img_metas = [ds.metainfo for ds in batch_data_samples]
         assert img.dim() == 5, 'multi-view input (B, n_views, C, H, W)'
@@ -134,7 +131,30 @@ class SparseFeatureFusionSingleStage3DDetector(nn.Module):
         img4 = img.reshape([-1] + list(img.shape)[2:]).to(self.compute_dtype)
         if not img4.is_contiguous(memory_format=torch.channels_last):
             img4 = img4.contiguous(memory_format=torch.channels_last)
-        img_features = self.backbone(img4)
+
+        # Two streams: the dense per-view 2D backbone runs on a side stream while the main stream builds the coordinate
+        # plan (whose row-count read-backs synchronise only the main stream) and runs the sparse 3D backbone; they
+        # join before point painting. Autograd replays the same stream assignment in backward.
+        side = None
+        if img4.is_cuda and self.overlap_2d_3d:
+            main = torch.cuda.current_stream()
+            if self._side_stream is None or self._side_stream.device != img4.device:
+                self._side_stream = torch.cuda.Stream(device=img4.device)
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                img_features = self.backbone(img4)
+        else:
+            img_features = self.backbone(img4)
+
+        coordinates, features = self.voxelize(points)
+        x = SP.SparseTensor(coordinates=coordinates, features=features.to(self.compute_dtype), batch_size=len(points))
+        x = self.backbone_3d(x)
+        num_levels = len(x)
+        if side is not None:
+            main.wait_stream(side)
+            for f in img_features:
+                f.record_stream(main)
 
         dev = img.device
         metas = pack_paint_metas(batch_img_metas, dev)
