@@ -40,8 +40,8 @@ SIGNATURES = {
     'esb_bias_act_fwd': ('ppppqiiip', 'i'),
     'esb_act_bwd': ('pppqiip', 'i'),
     'esb_paint_meta_bytes': ('', 'i'),
-    'esb_paint_fwd': ('pqfppipiiiffppip', 'i'),
-    'esb_paint_bwd': ('pqfppipiiiffpip', 'i'),
+    'esb_paint_fwd': ('pppqfppipiiiffppip', 'i'),
+    'esb_paint_bwd': ('pppqfppipiiiffpip', 'i'),
     'esb_fcaf3d_targets_workspace_bytes': ('iii', 'z'),
     'esb_fcaf3d_targets': ('ppiippppp' + 'iiiii' + 'pppp' + 'pzp', 'i'),
     'esb_focal_loss_fwd': ('ppqiffppip', 'i'),

@@ -75,19 +75,29 @@ __device__ __forceinline__ int project(const float* __restrict__ P, const EsbPai
   return iy * Wf + ix;
 }
 
-__device__ __forceinline__ void point_of(const int* __restrict__ coords, long long n, float voxel_size,
+// A point is either a voxel row (coords int32 [b,x,y,z] -> xyz * voxel_size) or, when fpts != NULL, an explicit fp32
+// location fpts[n] of scan fbatch[n] (NULL: scan 0) — the prior-grid centres of the occupancy model
+// (embodiedscan/models/detectors/dense_fusion_occ.py:156-202).
+__device__ __forceinline__ void point_of(const int* __restrict__ coords, const float* __restrict__ fpts,
+                                         const int* __restrict__ fbatch, long long n, float voxel_size,
                                          const EsbPaintMeta* __restrict__ metas, int* b, float* x, float* y, float* z) {
-  int4 c = reinterpret_cast<const int4*>(coords)[n];
-  *b = c.x;
-  *x = __fmul_rn((float)c.y, voxel_size);
-  *y = __fmul_rn((float)c.z, voxel_size);
-  *z = __fmul_rn((float)c.w, voxel_size);
-  apply_ops(metas[c.x], *x, *y, *z);
+  if (fpts != nullptr) {
+    *b = fbatch ? fbatch[n] : 0;
+    *x = fpts[3 * n]; *y = fpts[3 * n + 1]; *z = fpts[3 * n + 2];
+  } else {
+    int4 c = reinterpret_cast<const int4*>(coords)[n];
+    *b = c.x;
+    *x = __fmul_rn((float)c.y, voxel_size);
+    *y = __fmul_rn((float)c.z, voxel_size);
+    *z = __fmul_rn((float)c.w, voxel_size);
+  }
+  apply_ops(metas[*b], *x, *y, *z);
 }
 
 // feat: (B*V, Hf, Wf, C) channels-last ; out: (N, C)
 template <typename T>
-__global__ void paint_fwd_kernel(const int* __restrict__ coords, long long N, float voxel_size,
+__global__ void paint_fwd_kernel(const int* __restrict__ coords, const float* __restrict__ fpts,
+                                 const int* __restrict__ fbatch, long long N, float voxel_size,
                                  const EsbPaintMeta* __restrict__ metas, const float* __restrict__ proj, int V,
                                  const T* __restrict__ feat, int Hf, int Wf, int C, float pad_h, float pad_w,
                                  T* __restrict__ out, int* __restrict__ valid_count) {
@@ -95,7 +105,7 @@ __global__ void paint_fwd_kernel(const int* __restrict__ coords, long long N, fl
   const long long n = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
   int b; float x, y, z;
-  point_of(coords, n, voxel_size, metas, &b, &x, &y, &z);
+  point_of(coords, fpts, fbatch, n, voxel_size, metas, &b, &x, &y, &z);
   const EsbPaintMeta& m = metas[b];
   float acc[16];  // up to C = 512 : 16 channels per lane, channel = lane + 32*j ... stored strided
 #pragma unroll
@@ -129,7 +139,8 @@ __global__ void paint_fwd_kernel(const int* __restrict__ coords, long long N, fl
 
 // dfeat (fp32, same layout as feat) += dout[n] / count for every view whose nearest pixel is inside the map
 template <typename T>
-__global__ void paint_bwd_kernel(const int* __restrict__ coords, long long N, float voxel_size,
+__global__ void paint_bwd_kernel(const int* __restrict__ coords, const float* __restrict__ fpts,
+                                 const int* __restrict__ fbatch, long long N, float voxel_size,
                                  const EsbPaintMeta* __restrict__ metas, const float* __restrict__ proj, int V,
                                  const T* __restrict__ dout, int Hf, int Wf, int C, float pad_h, float pad_w,
                                  float* __restrict__ dfeat) {
@@ -137,7 +148,7 @@ __global__ void paint_bwd_kernel(const int* __restrict__ coords, long long N, fl
   const long long n = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
   int b; float x, y, z;
-  point_of(coords, n, voxel_size, metas, &b, &x, &y, &z);
+  point_of(coords, fpts, fbatch, n, voxel_size, metas, &b, &x, &y, &z);
   const EsbPaintMeta& m = metas[b];
   // first pass: count valid views
   int count = 0;
@@ -176,7 +187,8 @@ __global__ void paint_bwd_kernel(const int* __restrict__ coords, long long N, fl
 
 extern "C" int esb_paint_meta_bytes() { return (int)sizeof(EsbPaintMeta); }
 
-extern "C" int esb_paint_fwd(const int* coords, long long N, float voxel_size, const void* metas, const float* proj,
+extern "C" int esb_paint_fwd(const int* coords, const float* fpts, const int* fbatch, long long N, float voxel_size,
+                             const void* metas, const float* proj,
                              int V, const void* feat, int Hf, int Wf, int C, float pad_h, float pad_w, void* out,
                              int* valid_count, int dtype, void* stream) {
   ESB_CHECK_ARG(C >= 1 && C <= 512, "esb_paint_fwd: C must be in [1,512]");
@@ -184,30 +196,31 @@ extern "C" int esb_paint_fwd(const int* coords, long long N, float voxel_size, c
   if (N == 0) return ESB_OK;
   int grid = esb_div_up(N * 32, 256);
   if (dtype == ESB_F32)
-    paint_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(coords, N, voxel_size, (const EsbPaintMeta*)metas, proj,
+    paint_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(coords, fpts, fbatch, N, voxel_size, (const EsbPaintMeta*)metas, proj,
                                                                      V, (const float*)feat, Hf, Wf, C, pad_h, pad_w,
                                                                      (float*)out, valid_count);
   else
     paint_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        coords, N, voxel_size, (const EsbPaintMeta*)metas, proj, V, (const __nv_bfloat16*)feat, Hf, Wf, C, pad_h, pad_w,
+        coords, fpts, fbatch, N, voxel_size, (const EsbPaintMeta*)metas, proj, V, (const __nv_bfloat16*)feat, Hf, Wf, C, pad_h, pad_w,
         (__nv_bfloat16*)out, valid_count);
   ESB_CUDA_LAUNCH_CHECK("paint_fwd_kernel");
   return ESB_OK;
 }
 
 // dfeat must be zero-initialised fp32 with the layout of feat.
-extern "C" int esb_paint_bwd(const int* coords, long long N, float voxel_size, const void* metas, const float* proj,
+extern "C" int esb_paint_bwd(const int* coords, const float* fpts, const int* fbatch, long long N, float voxel_size,
+                             const void* metas, const float* proj,
                              int V, const void* dout, int Hf, int Wf, int C, float pad_h, float pad_w, float* dfeat,
                              int dtype, void* stream) {
   ESB_CHECK_ARG(C >= 1 && C <= 512, "esb_paint_bwd: C must be in [1,512]");
   if (N == 0) return ESB_OK;
   int grid = esb_div_up(N * 32, 256);
   if (dtype == ESB_F32)
-    paint_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(coords, N, voxel_size, (const EsbPaintMeta*)metas, proj,
+    paint_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(coords, fpts, fbatch, N, voxel_size, (const EsbPaintMeta*)metas, proj,
                                                                      V, (const float*)dout, Hf, Wf, C, pad_h, pad_w, dfeat);
   else
     paint_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        coords, N, voxel_size, (const EsbPaintMeta*)metas, proj, V, (const __nv_bfloat16*)dout, Hf, Wf, C, pad_h, pad_w,
+        coords, fpts, fbatch, N, voxel_size, (const EsbPaintMeta*)metas, proj, V, (const __nv_bfloat16*)dout, Hf, Wf, C, pad_h, pad_w,
         dfeat);
   ESB_CUDA_LAUNCH_CHECK("paint_bwd_kernel");
   return ESB_OK;

@@ -104,30 +104,30 @@ def pack_projections(img_metas: Sequence[dict], coord_type: str, device) -> torc
 class _Paint(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, feat, coords, metas, proj, voxel_size, pad_hw, V):
-        """feat (B*V, C, Hf, Wf) in channels_last memory; coords (N,4) int32 -> (N, C)."""
+    def forward(ctx, feat, coords, fpts, fbatch, metas, proj, voxel_size, pad_hw, V):
+        """feat (B*V, C, Hf, Wf) in channels_last memory; coords (N,4) int32 voxel rows OR fpts (N,3) fp32 -> (N, C)."""
         assert feat.is_contiguous(memory_format=torch.channels_last) or feat.shape[1] == 1
         BV, C, Hf, Wf = feat.shape
-        N = coords.shape[0]
+        N = coords.shape[0] if coords is not None else fpts.shape[0]
         out = torch.empty((N, C), dtype=feat.dtype, device=feat.device)
-        call('esb_paint_fwd', ptr(coords), N, voxel_size, ptr(metas), ptr(proj), V, ptr(feat), Hf, Wf, C,
-             float(pad_hw[0]), float(pad_hw[1]), ptr(out), None, _ffi.dtype_code(feat.dtype), stream())
-        ctx.save_for_backward(coords, metas, proj)
-        ctx.meta = (voxel_size, pad_hw, V, feat.shape, feat.dtype)
+        call('esb_paint_fwd', ptr(coords), ptr(fpts), ptr(fbatch), N, voxel_size, ptr(metas), ptr(proj), V, ptr(feat), Hf, Wf,
+             C, float(pad_hw[0]), float(pad_hw[1]), ptr(out), None, _ffi.dtype_code(feat.dtype), stream())
+        ctx.pts = (coords, fpts, fbatch, metas, proj)
+        ctx.meta = (voxel_size, pad_hw, V, feat.shape, feat.dtype, N)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        coords, metas, proj = ctx.saved_tensors
-        voxel_size, pad_hw, V, shape, dtype = ctx.meta
+        coords, fpts, fbatch, metas, proj = ctx.pts
+        voxel_size, pad_hw, V, shape, dtype, N = ctx.meta
         if not ctx.needs_input_grad[0]:
-            return None, None, None, None, None, None, None
+            return (None, ) * 9
         BV, C, Hf, Wf = shape
         dout = dout.contiguous()
         dfeat = torch.zeros((BV, Hf, Wf, C), dtype=torch.float32, device=dout.device)
-        call('esb_paint_bwd', ptr(coords), coords.shape[0], voxel_size, ptr(metas), ptr(proj), V, ptr(dout), Hf, Wf, C,
-             float(pad_hw[0]), float(pad_hw[1]), ptr(dfeat), _ffi.dtype_code(dout.dtype), stream())
-        return dfeat.permute(0, 3, 1, 2).to(dtype), None, None, None, None, None, None
+        call('esb_paint_bwd', ptr(coords), ptr(fpts), ptr(fbatch), N, voxel_size, ptr(metas), ptr(proj), V, ptr(dout), Hf, Wf,
+             C, float(pad_hw[0]), float(pad_hw[1]), ptr(dfeat), _ffi.dtype_code(dout.dtype), stream())
+        return (dfeat.permute(0, 3, 1, 2).to(dtype), ) + (None, ) * 8
 
 
 def paint_points(feat: torch.Tensor, coords: torch.Tensor, metas: torch.Tensor, proj: torch.Tensor, voxel_size: float,
@@ -135,4 +135,12 @@ def paint_points(feat: torch.Tensor, coords: torch.Tensor, metas: torch.Tensor, 
     """Image features (B*V, C, Hf, Wf) sampled at the voxel centres ``coords[:,1:] * voxel_size`` of every scan."""
     if not feat.is_contiguous(memory_format=torch.channels_last):
         feat = feat.contiguous(memory_format=torch.channels_last)
-    return _Paint.apply(feat, coords, metas, proj, float(np.float32(voxel_size)), pad_hw, n_views)
+    return _Paint.apply(feat, coords, None, None, metas, proj, float(np.float32(voxel_size)), pad_hw, n_views)
+
+
+def paint_float_points(feat: torch.Tensor, points: torch.Tensor, batch: torch.Tensor, metas: torch.Tensor,
+                       proj: torch.Tensor, pad_hw, n_views: int) -> torch.Tensor:
+    """Same kernel on explicit fp32 locations ``points`` (N,3) of scans ``batch`` (N) int32 (None: scan 0)."""
+    if not feat.is_contiguous(memory_format=torch.channels_last):
+        feat = feat.contiguous(memory_format=torch.channels_last)
+    return _Paint.apply(feat, None, points.float().contiguous(), batch, metas, proj, 1.0, pad_hw, n_views)

@@ -89,10 +89,14 @@ int esb_act_bwd(const void* dy, const void* y, void* dx, long long n, int act, i
 /* ---- point painting (batch_point_sample + apply_3d_transformation + batch_points_cam2img + F.grid_sample;
  * embodiedscan/models/layers/fusion_layers/point_fusion.py:208-311, structures/bbox_3d/utils.py:289-332) -------- */
 int esb_paint_meta_bytes(void);
-int esb_paint_fwd(const int* coords, long long N, float voxel_size, const void* metas, const float* proj, int V,
+/* points: voxel rows `coords` (xyz * voxel_size) or, when fpts != NULL, explicit fp32 locations fpts (N,3) of scans
+ * fbatch (N) (NULL: scan 0) — the prior grid of the occupancy model (dense_fusion_occ.py:156-202) */
+int esb_paint_fwd(const int* coords, const float* fpts, const int* fbatch, long long N, float voxel_size,
+                  const void* metas, const float* proj, int V,
                   const void* feat, int Hf, int Wf, int C, float pad_h, float pad_w, void* out, int* valid_count,
                   int dtype, void* stream);
-int esb_paint_bwd(const int* coords, long long N, float voxel_size, const void* metas, const float* proj, int V,
+int esb_paint_bwd(const int* coords, const float* fpts, const int* fbatch, long long N, float voxel_size,
+                  const void* metas, const float* proj, int V,
                   const void* dout, int Hf, int Wf, int C, float pad_h, float pad_w, float* dfeat, int dtype,
                   void* stream);
 
