@@ -77,6 +77,9 @@ class Det3DDataPreprocessor(nn.Module):
             for ds in data_samples:
                 if 'gt_instances_3d' in ds:
                     ds.gt_instances_3d.to(dev)
+                for k in ('gt_occupancy', 'gt_occupancy_masks'):
+                    if k in ds:
+                        setattr(ds, k, getattr(ds, k).to(dev))
         return {'inputs': out, 'data_samples': data_samples}
 
 

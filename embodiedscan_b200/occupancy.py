@@ -216,11 +216,11 @@ def sem_scal_loss(pred, ssc_target):
     nominator = (pm * onehot).sum(1)
     n_not = (1 - onehot).sum(1)
     present = n_tgt > 0
-    safe = lambda a, b: a / torch.where(b > 0, b, torch.ones_like(b))
-    loss_c = torch.where(sum_p > 0, _nlog(safe(nominator, sum_p)), torch.zeros_like(sum_p))
-    loss_c = loss_c + _nlog(safe(nominator, n_tgt))
-    spec = safe(((1 - pm) * (1 - onehot)).sum(1), n_not)
-    loss_c = loss_c + torch.where(n_not > 0, _nlog(spec), torch.zeros_like(spec))
+    one = torch.ones_like(sum_p)
+    # absent classes are skipped by the reference's loop: route them through log(1) so no inf/nan reaches autograd
+    ratio = lambda a, b, on: torch.where(on & (b > 0), a / torch.where(b > 0, b, one), one)
+    loss_c = _nlog(ratio(nominator, sum_p, present)) + _nlog(ratio(nominator, n_tgt, present)) + \
+        _nlog(ratio(((1 - pm) * (1 - onehot)).sum(1), n_not, present))
     count = present.float().sum()
     total = torch.where(present, loss_c, torch.zeros_like(loss_c)).sum()
     return torch.where(count > 0, total / torch.clamp(count, min=1.), total * 0)
@@ -348,6 +348,13 @@ class DenseFusionOccPredictor(nn.Module):
         return batch_data_samples
 
     def forward(self, inputs, data_samples=None, mode='tensor', **kwargs):
+        if self.compute_dtype == torch.float32 and torch.backends.cudnn.allow_tf32:
+            # fp32 is the parity arithmetic: keep the library convolutions out of TF32
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return self._forward(inputs, data_samples, mode, **kwargs)
+        return self._forward(inputs, data_samples, mode, **kwargs)
+
+    def _forward(self, inputs, data_samples, mode, **kwargs):
         if mode == 'loss':
             return self.loss(inputs, data_samples, **kwargs)
         if mode == 'predict':

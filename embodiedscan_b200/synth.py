@@ -171,3 +171,56 @@ def mv_det3d_config(variant: str = 'C2') -> dict:
                        cls_loss=dict(type='mmdet.FocalLoss'), decouple_bbox_loss=True, decouple_groups=4,
                        decouple_weights=[0.2, 0.2, 0.2, 0.4]),
         coord_type='DEPTH', train_cfg=dict(), test_cfg=dict(nms_pre=1000, iou_thr=.5, score_thr=.01))
+
+
+# occupancy (BASELINE config C3): configs/occupancy/mv-occ_8xb1_embodiedscan-occ-80class.py:10-60
+def synth_occupancy(data_sample, point_cloud_range, n_voxels, num_classes: int = 81) -> torch.Tensor:
+    """Ground-truth occupancy (M,4) int64 [ix, iy, iz, label] of the non-empty voxels: voxels whose centre lies in a
+    ground-truth box get that box's class (1..num_classes-1), the floor layer gets class 1; empty voxels are omitted
+    (label 0 by construction in ``occ_multiscale_supervision``)."""
+    r = torch.tensor(point_cloud_range, dtype=torch.float32)
+    n = torch.tensor(n_voxels)
+    step = (r[3:] - r[:3]) / n
+    ii = torch.stack(torch.meshgrid(*[torch.arange(k) for k in n_voxels], indexing='ij'), -1).view(-1, 3)
+    ctr = r[:3] + (ii.float() + 0.5) * step
+    gt = data_sample.gt_instances_3d
+    boxes = gt.bboxes_3d.tensor.float().cpu()
+    rot = euler_angles_to_matrix(boxes[:, 6:9], 'ZXY')
+    local = torch.einsum('nbj,bjk->nbk', ctr[:, None] - boxes[None, :, :3], rot)       # R^T (p - c)
+    inside = (local.abs() <= boxes[None, :, 3:6] / 2).all(-1)
+    label = torch.zeros(ctr.shape[0], dtype=torch.long)
+    label[ctr[:, 2] < r[2] + step[2]] = 1
+    for b in range(boxes.shape[0]):
+        label[inside[:, b]] = int(gt.labels_3d[b]) % (num_classes - 1) + 1
+    nz = label > 0
+    return torch.cat([ii[nz], label[nz, None]], 1)
+
+
+def mv_occ_config(variant: str = 'C3') -> dict:
+    """C3: full-width ResNet-50 + FPN + MinkResNet34 on a 40x40x16 grid (the published config). 'C3-small': ResNet-18/16,
+    MinkResNet14 and an 8x8x4 grid for parity tests the CPU oracle finishes in seconds."""
+    if variant == 'C3':
+        depth2d, base, depth3d, n_vox = 50, 64, 34, [40, 40, 16]
+        prior, pcr = [-3.2, -3.2, -1.28, 3.2, 3.2, 1.28], [-3.2, -3.2, -0.78, 3.2, 3.2, 1.78]
+        c2d, c3d, fpn_out, neck_out = [256, 512, 1024, 2048], 512, 256, 128
+    elif variant == 'C3-small':
+        depth2d, base, depth3d, n_vox = 18, 16, 14, [8, 8, 4]
+        prior, pcr = [-3.2, -3.2, -1.28, 3.2, 3.2, 1.28], [-3.2, -3.2, -0.78, 3.2, 3.2, 1.78]
+        c2d, c3d, fpn_out, neck_out = [16, 32, 64, 128], 512, 32, 32
+    else:
+        raise KeyError(variant)
+    return dict(
+        type='DenseFusionOccPredictor', use_valid_mask=False, use_xyz_feat=True, point_cloud_range=pcr,
+        data_preprocessor=dict(type='Det3DDataPreprocessor', mean=[123.675, 116.28, 103.53],
+                               std=[58.395, 57.12, 57.375], bgr_to_rgb=True, pad_size_divisor=32),
+        backbone=dict(type='mmdet.ResNet', depth=depth2d, base_channels=base, num_stages=4, out_indices=(0, 1, 2, 3),
+                      frozen_stages=1, norm_cfg=dict(type='BN', requires_grad=False), norm_eval=True, style='pytorch'),
+        backbone_3d=dict(type='MinkResNet', in_channels=3, depth=depth3d),
+        neck=dict(type='mmdet.FPN', in_channels=c2d, out_channels=fpn_out, num_outs=4),
+        neck_3d=dict(type='IndoorImVoxelNeck', in_channels=fpn_out + c3d, out_channels=neck_out, n_blocks=[1, 1, 1]),
+        bbox_head=dict(type='ImVoxelOccHead', volume_h=[n_vox[0], n_vox[0] // 2, n_vox[0] // 4],
+                       volume_w=[n_vox[1], n_vox[1] // 2, n_vox[1] // 4],
+                       volume_z=[n_vox[2], n_vox[2] // 2, n_vox[2] // 4], num_classes=81,
+                       in_channels=[neck_out] * 3, use_semantic=True),
+        prior_generator=dict(type='AlignedAnchor3DRangeGenerator', ranges=[prior], rotations=[.0]),
+        n_voxels=n_vox, coord_type='DEPTH')

@@ -158,3 +158,66 @@ def test_arena_direct_gradients_equal_autograd(dtype):
         noise = rel_err(models[0], models[1])
         err = rel_err(models[0], models[2])
         assert err <= 3.0 * noise + 2e-2, (err, noise)
+
+
+# ---- occupancy: DenseFusionOccPredictor on an 8x8x4 grid against oracle/occ_ref.py -------------------
+def _setup_occ(seed=0):
+    from embodiedscan_b200 import MODELS
+    from embodiedscan_b200.synth import mv_occ_config, synth_batch, synth_occupancy
+    from oracle import model_ref as M
+    torch.manual_seed(seed)
+    cfg = mv_occ_config('C3-small')
+    model = MODELS.build(cfg).to(DEV)
+    batch = synth_batch(1, 1, n_views=2, H=240, W=320, n_points=4000)
+    for ds in batch['data_samples']:
+        ds.gt_occupancy = synth_occupancy(ds, cfg['point_cloud_range'], cfg['n_voxels'])
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    return cfg, model, batch, sd, imgs
+
+
+def test_occupancy_loss_and_gradients_match_oracle():
+    from oracle import occ_ref as R
+    cfg, model, batch, sd, imgs = _setup_occ()
+    model.train()
+    watch = ['bbox_head.occ.0.weight', 'bbox_head.occ.2.weight', 'neck_3d.down_layer_1.0.conv1.weight',
+             'neck_3d.up_block_1.0.weight', 'neck.lateral_convs.0.conv.weight', 'neck.lateral_convs.3.conv.bias',
+             'backbone_3d.layer4.0.conv1.kernel', 'backbone_3d.conv1.kernel', 'backbone.layer2.0.cb1.conv.weight']
+    for k in watch:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    ref = R.occ_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
+    sum(ref.values()).backward()
+    data = model.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the backward pass reads the global flag
+    try:
+        losses = model(**data, mode='loss')
+        sum(losses.values()).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert int((batch['data_samples'][0].gt_occupancy[:, 3] > 1).sum()) > 0, 'the grid must contain object voxels'
+    for k in ('loss_occ_0', 'loss_occ_1', 'loss_occ_2'):
+        a, b = float(losses[k]), float(ref[k])
+        assert abs(a - b) <= 1e-3 * max(abs(b), 1e-3), (k, a, b)
+    params = dict(model.named_parameters())
+    report = {}
+    for k in watch:
+        g, gr = params[k].grad.cpu(), sd[k].grad
+        report[k] = (float((g - gr).abs().max()) / max(float(gr.abs().max()), 1e-9),
+                     float((g - gr).norm()) / max(float(gr.norm()), 1e-9))
+    print('occupancy gradient parity (max-rel, l2-rel):', report)
+    for k, (mx, l2) in report.items():
+        assert mx <= 5e-3 and l2 <= 5e-3, (k, mx, l2)
+
+
+def test_occupancy_predict_matches_oracle():
+    from oracle import occ_ref as R
+    cfg, model, batch, sd, imgs = _setup_occ(seed=1)
+    model.eval()
+    ref = R.occ_predict(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
+    out = model.val_step(dict(inputs=batch['inputs'], data_samples=batch['data_samples']))
+    pred = out[0].pred_occupancy.cpu()
+    assert pred.shape == tuple(cfg['n_voxels'])
+    agree = float((pred == ref[0]).float().mean())
+    assert agree >= 0.99, agree      # argmax over 81 near-tied random-init logits: allow isolated fp32 tie flips
