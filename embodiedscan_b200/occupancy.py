@@ -172,18 +172,29 @@ class IndoorImVoxelNeck(nn.Module):
 
 # ---- SurroundOcc losses (occ_loss.py) -------------------------------------------------------------------------------
 def occ_multiscale_supervision(gt_occ, ratio, gt_shape, gt_occupancy_masks=None):
-    gt = torch.zeros([gt_shape[0], gt_shape[2], gt_shape[3], gt_shape[4]], dtype=torch.long, device=gt_occ[0].device)
-    for i in range(gt.shape[0]):
-        coords = torch.div(gt_occ[i][:, :3].long(), ratio, rounding_mode='trunc')
-        gt[i, coords[:, 0], coords[:, 1], coords[:, 2]] = gt_occ[i][:, 3].long()
-        if gt_occupancy_masks is not None:
+    """occ_loss.py:7-29. At ratio > 1 several fine voxels land in one coarse cell; the reference's indexed assignment
+    leaves the winner to the device's write order. Frozen here to the sequential (CPU) order: the last row wins."""
+    B, X, Y, Z = gt_shape[0], gt_shape[2], gt_shape[3], gt_shape[4]
+    gt = torch.zeros([B, X * Y * Z], dtype=torch.long, device=gt_occ[0].device)
+    for i in range(B):
+        occ = gt_occ[i].long()
+        c = torch.div(occ[:, :3], ratio, rounding_mode='trunc')
+        lin = (c[:, 0] * Y + c[:, 1]) * Z + c[:, 2]
+        last = torch.full((X * Y * Z, ), -1, dtype=torch.long, device=occ.device)
+        last.scatter_reduce_(0, lin, torch.arange(occ.shape[0], device=occ.device), reduce='amax')
+        gt[i] = torch.where(last >= 0, occ[last.clamp(min=0), 3], gt[i])
+    gt = gt.view(B, X, Y, Z)
+    if gt_occupancy_masks is not None:
+        for i in range(B):
             gt[i][~gt_occupancy_masks[i]] = 255
     return gt
 
 
 def _nlog(x):
-    """F.binary_cross_entropy(x, ones) = -max(log x, -100)."""
-    return -torch.clamp(torch.log(x), min=-100.)
+    """F.binary_cross_entropy(x, ones): -max(log x, -100) with the library's bounded gradient at x == 0 (a scale whose
+    target set is empty yields exactly 0 there). The clamp guards the op's [0, 1] domain check against a 1-ulp overshoot."""
+    x = x.clamp(0., 1.)
+    return F.binary_cross_entropy(x, torch.ones_like(x), reduction='none')
 
 
 def geo_scal_loss(pred, ssc_target, semantic=True):

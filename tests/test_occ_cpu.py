@@ -72,3 +72,16 @@ def test_fpn_and_neck_match_oracle():
     assert [tuple(o.shape[2:]) for o in outs] == [(8, 8, 4), (4, 4, 2), (2, 2, 1)]
     for a, b in zip(outs, ref):
         assert torch.allclose(a, b, atol=1e-4), (a - b).abs().max()
+
+
+def test_scal_losses_full_grid_gradients_finite():
+    """A coarse scale whose voxels are all occupied makes specificity exactly 0 (log clamp active): gradients must stay
+    finite and equal to the oracle's."""
+    g = torch.Generator().manual_seed(5)
+    pred = torch.randn(1, 7, 2, 2, 1, generator=g)
+    tgt = torch.tensor([1, 2, 3, 3]).view(1, 2, 2, 1)
+    p1, p2 = pred.clone().requires_grad_(), pred.clone().requires_grad_()
+    (OCC.geo_scal_loss(p1, tgt) + OCC.sem_scal_loss(p1, tgt)).backward()
+    (R.geo_scal_loss(p2, tgt) + R.sem_scal_loss(p2, tgt)).backward()
+    assert torch.isfinite(p1.grad).all()
+    assert torch.allclose(p1.grad, p2.grad, rtol=1e-4, atol=1e-6)
