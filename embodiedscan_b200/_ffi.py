@@ -50,6 +50,7 @@ SIGNATURES = {
     'esb_nms_bev_segmented': ('ppiifipp', 'i'),
     'esb_iou_bev_pairwise': ('pipiipp', 'i'),
     'esb_box3d_overlap': ('pipippp', 'i'),
+    'esb_hungarian_batch': ('ppiiippp', 'i'),
     'esb_img_normalize': ('piiiiippiipip', 'i'),
     'esb_unproject_depth_workspace_bytes': ('iii', 'z'),
     'esb_unproject_depth': ('piiifpppppzp', 'i'),

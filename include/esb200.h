@@ -126,6 +126,15 @@ int esb_iou_bev_pairwise(const float* a, int na, const float* b, int nb, int rot
 int esb_box3d_overlap(const float* corners1, int n1, const float* corners2, int n2, float* vol, float* iou,
                       void* stream);
 
+/* ---- batched one-to-one assignment (HungarianAssigner3D.assign: hungarian_assigner.py:110-126 -> scipy
+ * linear_sum_assignment on the host, 7 layers x batch times per iteration from grounding_head.py:398).
+ * cost: (n_problems, n_pred, ld_gt) fp32, problem p uses columns [0, n_gt[p]); n_gt[p] <= ld_gt <= n_pred.
+ * NaN/+inf -> 100, -inf -> -100 as torch.nan_to_num in the reference. pred_to_gt: (n_problems, n_pred) int32, the
+ * 0-based target matched to each prediction or -1; gt_to_pred (nullable): (n_problems, ld_gt) int32, the inverse map
+ * (-1 beyond n_gt[p]). One launch, one CTA per problem. ---- */
+int esb_hungarian_batch(const float* cost, const int* n_gt, int n_problems, int n_pred, int ld_gt, int* pred_to_gt,
+                        int* gt_to_pred, void* stream);
+
 /* ---- input side: Det3DDataPreprocessor image path (data_preprocessor.py:249-264, utils.py:9-63) and the
  * depth->points unprojection (datasets/transforms/points.py:30-81, multiview.py:139-169) ------------------------- */
 int esb_img_normalize(const unsigned char* src, int n_img, int H, int W, int Hp, int Wp, const float* mean3_host,
