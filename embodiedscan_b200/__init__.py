@@ -8,6 +8,7 @@ from . import sparse  # noqa: F401
 from .backbones import MinkResNet, ResNet  # noqa: F401
 from .dense_heads import BBoxCDLoss, FCAF3DHeadRotMat  # noqa: F401
 from .detectors import Det3DDataPreprocessor, SparseFeatureFusionSingleStage3DDetector  # noqa: F401
+from .grounding import GroundingHead, MinkNeck, SparseFeatureFusion3DGrounder  # noqa: F401
 from .occupancy import DenseFusionOccPredictor, ImVoxelOccHead, IndoorImVoxelNeck  # noqa: F401
 from .structures import Det3DDataSample, EulerDepthInstance3DBoxes, InstanceData  # noqa: F401
 

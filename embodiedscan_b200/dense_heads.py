@@ -56,11 +56,33 @@ class FocalLoss(nn.Module):
         assert use_sigmoid and reduction == 'mean'
         self.gamma, self.alpha, self.loss_weight = gamma, alpha, loss_weight
 
-    def forward(self, pred, target, avg_factor=None, row_weight=None):
-        """sum(focal) / avg_factor, or sum(row_weight[r] * focal[r, :]) when per-row weights are given."""
+    def forward(self, pred, target, weight=None, avg_factor=None, row_weight=None):
+        """Integer targets (N,) on (N,C) logits: mmcv's CUDA op semantics, sum(focal) / avg_factor, or
+        sum(row_weight[r] * focal[r, :]) when per-row weights are given. Float targets of pred's shape: mmdet's
+        ``py_sigmoid_focal_loss`` (soft / token-level targets, the grounding head's call, grounding_head.py:760-763)."""
+        if target.is_floating_point() and target.shape == pred.shape:
+            return sigmoid_focal_loss_soft(pred, target, weight, self.gamma, self.alpha, avg_factor) * self.loss_weight
         if row_weight is None:
+            if not torch.is_tensor(avg_factor):
+                avg_factor = torch.tensor(float(avg_factor), device=pred.device)
             row_weight = (1.0 / avg_factor.to(torch.float32).reshape(1)).expand(pred.shape[0]).contiguous()
         return _Focal.apply(pred, target, row_weight, self.gamma, self.alpha) * self.loss_weight
+
+
+def sigmoid_focal_loss_soft(pred, target, weight=None, gamma=2.0, alpha=0.25, avg_factor=None):
+    """mmdet ``py_sigmoid_focal_loss`` + ``weight_reduce_loss(reduction='mean')`` (†upstream): with an avg_factor the
+    result is sum / (avg_factor + eps_fp32), else the plain mean."""
+    pred = pred.float()
+    p = pred.sigmoid()
+    target = target.type_as(pred)
+    pt = (1 - p) * target + p * (1 - target)
+    focal_weight = (alpha * target + (1 - alpha) * (1 - target)) * pt.pow(gamma)
+    loss = F.binary_cross_entropy_with_logits(pred, target, reduction='none') * focal_weight
+    if weight is not None:
+        loss = loss * weight
+    if avg_factor is None:
+        return loss.mean()
+    return loss.sum() / (avg_factor + torch.finfo(torch.float32).eps)
 
 
 class _Focal(torch.autograd.Function):

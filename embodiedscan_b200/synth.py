@@ -224,3 +224,68 @@ def mv_occ_config(variant: str = 'C3') -> dict:
                        in_channels=[neck_out] * 3, use_semantic=True),
         prior_generator=dict(type='AlignedAnchor3DRangeGenerator', ranges=[prior], rotations=[.0]),
         n_voxels=n_vox, coord_type='DEPTH')
+
+
+# grounding (BASELINE config C4): configs/grounding/mv-grounding_8xb12_embodiedscan-vg-9dof.py:18-88
+_NOUNS = ['chair', 'table', 'cabinet', 'lamp', 'sofa', 'shelf', 'monitor', 'plant', 'box', 'bed']
+
+
+def add_grounding_prompt(data_sample, n_targets: int = 1, seed: int = 0):
+    """Turn a detection sample into a visual-grounding sample: keep ``n_targets`` of its boxes as the targets of a
+    synthetic prompt and attach ``text`` + ``tokens_positive`` (character spans of each target's phrase), the fields
+    ``MultiView3DGroundingDataset`` provides (embodiedscan/datasets/mv_3dvg_dataset.py †)."""
+    gen = torch.Generator().manual_seed(977 + seed)
+    gt = data_sample.gt_instances_3d
+    n = len(gt.bboxes_3d)
+    pick = torch.randperm(n, generator=gen)[:n_targets]
+    words = [_NOUNS[int(gt.labels_3d[i]) % len(_NOUNS)] for i in pick]
+    text, spans = 'find the ', []
+    for k, w in enumerate(words):
+        if k:
+            text += ' and the '
+        spans.append([[len(text), len(text) + len(w)]])
+        text += w
+    text += ' that is close to the wall.'
+    new = InstanceData()
+    new.bboxes_3d = EulerDepthInstance3DBoxes(gt.bboxes_3d.tensor[pick], box_dim=9)
+    new.labels_3d = gt.labels_3d[pick]
+    data_sample.gt_instances_3d = new
+    data_sample.text = text
+    data_sample.tokens_positive = spans
+    return data_sample
+
+
+def mv_grounding_config(variant: str = 'C4') -> dict:
+    """C4: the published grounding model. 'C4-small': ResNet-18/16 + MinkResNet14, 2 decoder layers, 32 queries and a
+    prune threshold low enough to exercise pruning — for parity tests the CPU oracle finishes in seconds."""
+    if variant == 'C4':
+        depth2d, depth3d, in_ch, nq, n_layers, ffn, prune, T = 50, 34, [128, 256, 512, 1024], 256, 6, 2048, 1000, 256
+    elif variant == 'C4-small':
+        depth2d, depth3d, in_ch, nq, n_layers, ffn, prune, T = 18, 14, [80, 160, 320, 640], 32, 2, 256, 150, 32
+    else:
+        raise KeyError(variant)
+    attn = dict(embed_dims=256, num_heads=8, dropout=0.0)
+    return dict(
+        type='SparseFeatureFusion3DGrounder', num_queries=nq, voxel_size=0.01,
+        data_preprocessor=dict(type='Det3DDataPreprocessor', mean=[123.675, 116.28, 103.53],
+                               std=[58.395, 57.12, 57.375], bgr_to_rgb=True, pad_size_divisor=32),
+        backbone=dict(type='mmdet.ResNet', depth=depth2d, base_channels=16, num_stages=4, out_indices=(0, 1, 2, 3),
+                      frozen_stages=1, norm_cfg=dict(type='BN', requires_grad=False), norm_eval=True, style='pytorch'),
+        backbone_3d=dict(type='MinkResNet', in_channels=3, depth=depth3d), use_xyz_feat=True,
+        neck_3d=dict(type='MinkNeck', num_classes=1, in_channels=in_ch, out_channels=256, voxel_size=0.01,
+                     pts_prune_threshold=prune),
+        decoder=dict(num_layers=n_layers, return_intermediate=True,
+                     layer_cfg=dict(self_attn_cfg=dict(attn), cross_attn_text_cfg=dict(attn), cross_attn_cfg=dict(attn),
+                                    ffn_cfg=dict(embed_dims=256, feedforward_channels=ffn, ffn_drop=0.0)),
+                     post_norm_cfg=None),
+        bbox_head=dict(type='GroundingHead', num_classes=256, num_pred_layer=n_layers + 1, sync_cls_avg_factor=True,
+                       decouple_bbox_loss=True, decouple_groups=4, share_pred_layer=True,
+                       decouple_weights=[0.2, 0.2, 0.2, 0.4],
+                       contrastive_cfg=dict(max_text_len=T, log_scale='auto', bias=True),
+                       loss_cls=dict(type='mmdet.FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+                       loss_bbox=dict(type='BBoxCDLoss', mode='l1', loss_weight=1.0, group='g8')),
+        coord_type='DEPTH',
+        train_cfg=dict(assigner=dict(type='HungarianAssigner3D', match_costs=[
+            dict(type='BinaryFocalLossCost', weight=1.0), dict(type='BBox3DL1Cost', weight=2.0),
+            dict(type='IoU3DCost', weight=2.0)])),
+        test_cfg=None)
