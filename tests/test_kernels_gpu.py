@@ -428,6 +428,31 @@ def test_box3d_overlap_9dof():
     assert float((ref_iou > 0.05).mean()) > 0.2, 'the test must exercise real overlaps'
 
 
+@pytest.mark.parametrize('n_pred,g_max,n_prob', [(256, 12, 84), (32, 32, 9), (700, 5, 4), (7, 1, 3)])
+def test_hungarian_batch_equals_scipy(n_pred, g_max, n_prob):
+    """One launch for every (layer, sample) problem vs scipy.optimize.linear_sum_assignment per problem (what
+    HungarianAssigner3D.assign runs on the host), incl. empty problems, n_gt == n_pred, and NaN/inf costs."""
+    from scipy.optimize import linear_sum_assignment
+    from embodiedscan_b200.grounding import hungarian_batch
+    g = np.random.RandomState(n_pred + g_max)
+    cost = g.normal(0, 3, (n_prob, n_pred, g_max)).astype(np.float32)
+    cost[0, 0, 0], cost[0, 1, 0], cost[0, 2, 0] = np.nan, np.inf, -np.inf
+    n_gt = g.randint(0, g_max + 1, n_prob).astype(np.int32)
+    n_gt[0], n_gt[-1] = g_max, 0
+    p2g, g2p = hungarian_batch(torch.from_numpy(cost).to(_dev()), torch.from_numpy(n_gt).to(_dev()))
+    p2g, g2p = p2g.cpu().numpy(), g2p.cpu().numpy()
+    for p in range(n_prob):
+        k = int(n_gt[p])
+        ref = np.full(n_pred, -1)
+        inv = np.full(g_max, -1)
+        if k:
+            c = np.nan_to_num(cost[p, :, :k].astype(np.float64), nan=100.0, posinf=100.0, neginf=-100.0)
+            r, cidx = linear_sum_assignment(c)
+            ref[r], inv[cidx] = cidx, r
+        assert (p2g[p] == ref).all(), (p, k)
+        assert (g2p[p] == inv).all(), (p, k)
+
+
 # ------------------------------------------------------------------------------------------------ input side
 def test_img_normalize_bit_exact():
     from embodiedscan_b200 import Det3DDataPreprocessor

@@ -221,3 +221,89 @@ def test_occupancy_predict_matches_oracle():
     assert pred.shape == tuple(cfg['n_voxels'])
     agree = float((pred == ref[0]).float().mean())
     assert agree >= 0.99, agree      # argmax over 81 near-tied random-init logits: allow isolated fp32 tie flips
+
+
+# ---- grounding: SparseFeatureFusion3DGrounder against oracle/ground_ref.py -------------------------
+def _setup_ground(seed=0):
+    import warnings
+    from embodiedscan_b200 import MODELS
+    from embodiedscan_b200.synth import add_grounding_prompt, mv_grounding_config, synth_batch
+    from oracle import model_ref as M
+    torch.manual_seed(seed)
+    cfg = mv_grounding_config('C4-small')
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        model = MODELS.build(cfg).to(DEV)
+    with torch.no_grad():          # the reference zero-initialises the last regression layer: make it informative
+        for p in model.bbox_head.reg_branches[0][-1].parameters():
+            p.normal_(0, 0.05)
+    batch = synth_batch(1, 2, n_views=2, H=240, W=320, n_points=2000)
+    for i, ds in enumerate(batch['data_samples']):
+        add_grounding_prompt(ds, 1 + 2 * i, seed=i)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    return cfg, model, batch, sd, imgs
+
+
+def test_grounder_loss_and_gradients_match_oracle():
+    from oracle import ground_ref as R
+    cfg, model, batch, sd, imgs = _setup_ground()
+    model.train()
+    model.text_encoder.eval()      # RoBERTa's dropout is random in training mode (as in the reference): pin it here
+    data = model.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the backward pass reads the global flag
+    try:
+        losses = model(**data, mode='loss')
+        sum(losses.values()).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    # the text encoder is a library model on both sides: its hidden states are the oracle's input
+    with torch.no_grad():
+        tok = model.tokenizer.batch_encode_plus([d.text for d in batch['data_samples']], padding='longest').to(DEV)
+        hidden = model.text_encoder(**tok).last_hidden_state.float().cpu()
+    tmask = tok.attention_mask.bool().cpu()
+    pos_maps = [d.gt_instances_3d.positive_maps.cpu() for d in batch['data_samples']]
+    watch = ['bbox_head.reg_branches.0.4.weight', 'bbox_head.cls_branches.0.bias', 'text_feat_map.weight',
+             'decoder.layers.0.cross_attn.attn.in_proj_weight', 'decoder.layers.1.ffn.layers.1.weight',
+             'decoder.cross_posembed.position_embedding_head.0.weight', 'neck_3d.out_block_0.0.kernel',
+             'neck_3d.up_block_2.0.kernel', 'backbone_3d.conv1.kernel', 'backbone.layer2.0.cb1.conv.weight']
+    for k in watch:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    for i in range(1, 3):              # shared prediction layers: every index aliases entry 0
+        for k in list(sd):
+            if k.startswith(f'bbox_head.reg_branches.{i}.') or k.startswith(f'bbox_head.cls_branches.{i}.'):
+                sd[k] = sd[k.replace(f'_branches.{i}.', '_branches.0.')]
+    ref, ref_inds = R.grounder_loss(sd, cfg, [p.cpu() for p in batch['inputs']['points']], imgs, batch['data_samples'],
+                                    hidden, tmask, pos_maps)
+    sum(ref.values()).backward()
+    assert set(ref) == set(losses)
+    for k in ref:
+        a, b = float(losses[k].detach()), float(ref[k].detach())
+        assert abs(a - b) <= 1e-3 * max(abs(b), 1e-3), (k, a, b)
+    params = dict(model.named_parameters())
+    report = {}
+    for k in watch:
+        g, gr = params[k].grad.cpu(), sd[k].grad
+        report[k] = (float((g - gr).abs().max()) / max(float(gr.abs().max()), 1e-9),
+                     float((g - gr).norm()) / max(float(gr.norm()), 1e-9))
+    print('grounding gradient parity (max-rel, l2-rel):', report)
+    for k, (mx, l2) in report.items():
+        assert mx <= 5e-3 and l2 <= 5e-3, (k, mx, l2)
+
+
+def test_grounder_predict_matches_oracle():
+    from oracle import ground_ref as R
+    cfg, model, batch, sd, imgs = _setup_ground(seed=1)
+    model.eval()
+    out = model.val_step(dict(inputs=batch['inputs'], data_samples=batch['data_samples']))
+    with torch.no_grad():
+        tok = model.tokenizer.batch_encode_plus([d.text for d in batch['data_samples']], padding='longest').to(DEV)
+        hidden = model.text_encoder(**tok).last_hidden_state.float().cpu()
+    cls, boxes = R.grounder_forward(sd, cfg, [p.cpu() for p in batch['inputs']['points']], imgs, batch['data_samples'],
+                                    hidden, tok.attention_mask.bool().cpu(), False)
+    for b, ds in enumerate(out):
+        ref_scores = cls[-1][b].sigmoid().max(-1)[0]
+        assert torch.allclose(ds.pred_instances_3d.scores_3d.cpu(), ref_scores, atol=1e-4)
+        assert torch.allclose(ds.pred_instances_3d.bboxes_3d.tensor.cpu(), boxes[-1][b], atol=1e-3, rtol=1e-3)
