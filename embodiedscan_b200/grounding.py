@@ -617,6 +617,8 @@ class SparseFeatureFusion3DGrounder(nn.Module):
         self.voxel_size, self.use_xyz_feat = voxel_size, use_xyz_feat
         self.freeze_text_encoder = freeze_text_encoder       # cfg: paramwise lr_mult=0 for 'text_encoder'
         self.tokenizer, self.text_encoder = build_text_modules('roberta-base')
+        if freeze_text_encoder:        # keeps the encoder out of the optimiser arena (no weight decay on frozen weights)
+            self.text_encoder.requires_grad_(False)
         self.decoder = SparseFeatureFusionTransformerDecoder(**decoder)
         self.embed_dims = self.decoder.embed_dims
         self.text_feat_map = nn.Linear(self.text_encoder.config.hidden_size, self.embed_dims, bias=True)
