@@ -403,6 +403,7 @@ class GroundingHead(nn.Module):
         """grounding_head.py:267-363: (B, nq, 3) anchor points + (B, nq, 9|12) regression -> (B, nq, 9) boxes."""
         assert points.dim() == bbox_pred.dim() == 3
         B, nq = points.shape[:2]
+        points, bbox_pred = points.float(), bbox_pred.float()
         if self.box_coder == 'baseline':
             center = bbox_pred[..., :3] + points
             size = torch.exp(bbox_pred[..., 3:6]).clamp(min=2e-2)
@@ -474,7 +475,7 @@ class GroundingHead(nn.Module):
         return cost
 
     def loss(self, hidden_states, all_layers_pred_bboxes, text_feats, text_token_mask, batch_data_samples):
-        cls_scores = self(hidden_states, text_feats, text_token_mask)[0]            # (Ly,B,nq,T)
+        cls_scores = self(hidden_states, text_feats, text_token_mask)[0].float()    # (Ly,B,nq,T)
         return self.loss_by_feat(cls_scores, all_layers_pred_bboxes, text_token_mask,
                                  [ds.gt_instances_3d for ds in batch_data_samples])
 
@@ -727,8 +728,12 @@ class SparseFeatureFusion3DGrounder(nn.Module):
         return dict(hidden_states=inter, all_layers_pred_bboxes=boxes)
 
     def forward_transformer(self, point_feats, scores, point_xyz, text_dict, batch_data_samples=None):
-        dec_in, head_in = self.pre_decoder(point_feats, scores, point_xyz, **text_dict)
-        head_in.update(self.forward_decoder(**dec_in))
+        # bf16 compute: the attention / FFN / contrastive contractions autocast to bf16 (LayerNorm and softmax stay fp32,
+        # box decoding and the losses are fp32 below); fp32 compute leaves the decoder in fp32 (the parity arithmetic)
+        amp = self.compute_dtype == torch.bfloat16 and point_feats[0].is_cuda
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+            dec_in, head_in = self.pre_decoder(point_feats, scores, point_xyz, **text_dict)
+            head_in.update(self.forward_decoder(**dec_in))
         return head_in
 
     # ---- entry points -----------------------------------------------------------------------------------------------
