@@ -287,7 +287,7 @@ class ResNet(nn.Module):
         return out
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
-        inv = {b: a for a, b in _RENAME.items()}
+        inv = {b: a for a, b in _RENAME.items() if not a.startswith('stem.')}     # stem handled explicitly below
         own = {k for k in super().state_dict(prefix=prefix).keys()}
         for k in list(state_dict.keys()):
             if not k.startswith(prefix) or k in own:

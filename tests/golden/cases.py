@@ -1,0 +1,28 @@
+"""Seeded inputs and configs of the golden cases, shared by `make_golden.py` (reference side) and the golden parity
+tests (oracle / CUDA side). Test infrastructure; imports nothing from `/root/reference` or `oracle/`."""
+import numpy as np
+import torch
+
+
+def division_safe(points, voxel_size=0.01):
+    """Keep the points whose voxel index is the same under true fp32 division (what torch-CPU evaluates for
+    `p / voxel_size`, the arithmetic the reference runs HERE) and under multiplication by the fp32 reciprocal (what
+    torch-CUDA evaluates, the arithmetic frozen by the oracle and the product) - so the fixture does not depend on it."""
+    p = points[:, :3].numpy().astype(np.float32)
+    a = np.floor(p / np.float32(voxel_size))
+    b = np.floor(p * (np.float32(1.0) / np.float32(voxel_size)))
+    return points[torch.from_numpy((a == b).all(1))]
+
+
+def det_inputs(n_scans, augment):
+    from embodiedscan_b200.synth import synth_batch
+    batch = synth_batch(1, n_scans, n_views=2, H=240, W=320, n_points=2000, augment=augment)
+    batch['inputs']['points'] = [division_safe(p) for p in batch['inputs']['points']]
+    return batch
+
+
+def det_config():
+    from embodiedscan_b200.synth import mv_det3d_config
+    cfg = mv_det3d_config('C1')
+    cfg['backbone_3d']['depth'] = 18                # the reference's MinkResNet has no depth 14 (mink_resnet.py:29-35)
+    return cfg

@@ -1,0 +1,168 @@
+"""Generate the golden vectors under tests/golden/*.npz by executing the REFERENCE'S OWN Python
+(`/root/reference/embodiedscan/**`, imported in place, never copied) on seeded inputs.
+
+Run in the dev container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py            # rewrites every fixture
+
+What runs on the reference side: its detector / backbone / head / fusion / loss / target / NMS-loop / transform code,
+unmodified.  What is stood in (tests/golden/refstubs.py, me_cpu.py): the un-installable third-party packages — plumbing
+stubs for mmengine/mmdet/mmcv, and `oracle/`-backed stand-ins for MinkowskiEngine, pytorch3d Euler conversions, mmcv
+nms3d.  So a fixture pins the reference's own arithmetic; third-party semantics stay "parity unpinned" (DESIGN.md §3).
+
+Weights are never stored: both sides rebuild them from (name, shape) with tests/golden/weights.py.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (HERE, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import refstubs  # noqa: E402
+
+refstubs.install()
+
+from cases import det_config, det_inputs  # noqa: E402
+from weights import adjust_fcaf3d_head, adjust_for_predict, fill_tensor  # noqa: E402
+
+
+def _np(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **{k: _np(v) for k, v in arrays.items()})
+    print(f'wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB,', ', '.join(sorted(arrays)))
+
+
+def fill_module(module, adjust=None):
+    """Overwrite every parameter / buffer of a reference module with the deterministic name-keyed fill."""
+    sd = module.state_dict()
+    manifest = [(k, tuple(v.shape)) for k, v in sd.items()]
+    new = {k: fill_tensor(k, s) for k, s in manifest}
+    module.load_state_dict(adjust(new) if adjust else new)
+    return manifest
+
+
+def calibrate_norms(model, run):
+    """Random running statistics make eval-mode activations explode layer after layer (saturated scores = ties
+    everywhere).  One no-grad pass with momentum 1 sets every BatchNorm's running statistics to the statistics of the
+    calibration batch; they are stored in the fixture ('calib/<name>') because they are data, not name-keyed fill."""
+    import torch.nn as nn
+    bns = [m for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)]
+    saved = [(m.momentum, m.training) for m in bns]
+    model.train()
+    for m in bns:
+        m.momentum, m.training = 1.0, True
+    with torch.no_grad():
+        run()
+    for m, (mom, tr) in zip(bns, saved):
+        m.momentum, m.training = mom, tr
+    return {'calib/' + k: v.clone() for k, v in model.state_dict().items()
+            if k.endswith(('running_mean', 'running_var'))}
+
+
+def manifest_arrays(manifest):
+    return dict(manifest_names=np.array([k for k, _ in manifest]),
+                manifest_shapes=np.array([','.join(map(str, s)) for _, s in manifest]))
+
+
+# ------------------------------------------------------------------------------------------------ shared inputs
+def ref_data_samples(data_samples):
+    """Product-side synthetic samples -> the reference's own Det3DDataElement / InstanceData / box classes."""
+    from embodiedscan.structures import EulerDepthInstance3DBoxes
+    from embodiedscan.utils.typing_config import Det3DDataElement
+    from mmengine.structures import InstanceData
+    out = []
+    for ds in data_samples:
+        meta = dict(ds.metainfo)
+        meta['box_type_3d'] = EulerDepthInstance3DBoxes
+        r = Det3DDataElement(metainfo=meta)
+        gt = InstanceData()
+        gt.bboxes_3d = EulerDepthInstance3DBoxes(ds.gt_instances_3d.bboxes_3d.tensor.clone(), box_dim=9,
+                                                 origin=(.5, .5, .5))
+        gt.labels_3d = ds.gt_instances_3d.labels_3d.clone()
+        r.gt_instances_3d = gt
+        out.append(r)
+    return out
+
+
+def build_reference_detector(cfg):
+    import copy
+
+    import embodiedscan.models  # noqa: F401  (registers everything)
+    from embodiedscan.registry import MODELS
+    from mmengine import ConfigDict
+    c = copy.deepcopy(cfg)
+    c.pop('data_preprocessor', None)
+    c['test_cfg'] = ConfigDict(c['test_cfg']) if c.get('test_cfg') else None
+    return MODELS.build(c)
+
+
+def gen_detector():
+    from oracle import model_ref as M
+    cfg = det_config()
+    model = build_reference_detector(cfg)
+    manifest = fill_module(model, adjust_fcaf3d_head)
+    out = manifest_arrays(manifest)
+    cal = det_inputs(1, False)
+    cal_imgs = M.preprocess_imgs(torch.stack(cal['inputs']['img']), cfg['data_preprocessor']['mean'],
+                                 cfg['data_preprocessor']['std'])
+    out.update(calibrate_norms(model, lambda: model(dict(points=cal['inputs']['points'], imgs=cal_imgs),
+                                                    ref_data_samples(cal['data_samples']), mode='loss')))
+    for tag, n_scans, augment in (('a', 1, False), ('b', 2, True)):
+        batch = det_inputs(n_scans, augment)
+        imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                                 cfg['data_preprocessor']['std'])      # a1 is pinned separately (gen_preprocess)
+        samples = ref_data_samples(batch['data_samples'])
+        model.train()
+        for p in model.parameters():
+            p.grad = None
+        losses = model(dict(points=batch['inputs']['points'], imgs=imgs), samples, mode='loss')
+        sum(losses.values()).backward()
+        for k, v in losses.items():
+            out[f'{tag}_{k}'] = v
+        params = dict(model.named_parameters())
+        for k in ('bbox_head.conv_cls.kernel', 'bbox_head.conv_reg.kernel', 'bbox_head.out_block_0.0.kernel',
+                  'bbox_head.up_block_1.0.kernel', 'backbone_3d.conv1.kernel', 'backbone_3d.layer2.0.conv1.kernel',
+                  'backbone_3d.layer1.0.norm1.bn.weight', 'backbone.layer2.0.conv1.weight', 'bbox_head.scales.1.scale'):
+            g = params[k].grad
+            out[f'{tag}_grad/{k}'] = g if g.numel() <= 4096 else g.flatten()[:: max(g.numel() // 4096, 1)][:4096]
+            out[f'{tag}_gradnorm/{k}'] = g.double().norm()
+        out[f'{tag}_n_points'] = np.array([len(p) for p in batch['inputs']['points']])
+    # predict: three classes clear the score threshold, top-50 per level exercises the top-k path
+    batch = det_inputs(1, False)
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    sd = adjust_for_predict(adjust_fcaf3d_head({k: fill_tensor(k, sh) for k, sh in manifest}))
+    sd.update({k[len('calib/'):]: v for k, v in out.items() if k.startswith('calib/')})   # train passes moved them
+    model.load_state_dict(sd)
+    model.bbox_head.test_cfg.nms_pre = 50
+    model.eval()
+    with torch.no_grad():
+        res = model(dict(points=batch['inputs']['points'], imgs=imgs), ref_data_samples(batch['data_samples']),
+                    mode='predict')
+    pred = res[0].pred_instances_3d
+    out['p_boxes'], out['p_scores'], out['p_labels'] = pred.bboxes_3d.tensor, pred.scores_3d, pred.labels_3d
+    print('detector: losses', {k: float(v.detach()) for k, v in out.items() if k.startswith(('a_loss', 'b_loss'))},
+          'predictions', len(pred.labels_3d))
+    save('detector_g1', **out)
+
+
+GENERATORS = dict(detector=gen_detector)
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or list(GENERATORS)
+    for w in which:
+        GENERATORS[w]()

@@ -1,0 +1,101 @@
+"""The oracle pinned against golden vectors produced by the REFERENCE'S OWN Python (tests/golden/make_golden.py ran
+`/root/reference/embodiedscan/**` in the dev container, third-party packages stood in; see tests/golden/README.md).
+
+These tests need neither a GPU nor /root/reference: weights are rebuilt from the stored manifest by the name-keyed fill,
+inputs by the seeded generators in tests/golden/cases.py.  Tolerances are fp32 round-off of a differently ordered
+evaluation of the same formulas (the reference uses bmm / grid_sample / index ops where the oracle spells out sums)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+if GOLD not in sys.path:
+    sys.path.insert(0, GOLD)
+
+from cases import det_config, det_inputs  # noqa: E402
+from weights import adjust_fcaf3d_head, adjust_for_predict, fill_state_dict  # noqa: E402
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + '.npz'), allow_pickle=False)
+
+
+def manifest(g):
+    return [(str(k), tuple(int(x) for x in str(s).split(',') if x)) for k, s in
+            zip(g['manifest_names'], g['manifest_shapes'])]
+
+
+def product_state_dict(cfg, g, adjust):
+    """Reference-named weights -> the product model (strict load = checkpoint compatibility) -> the
+    product's own state_dict, which is what the oracle is driven by."""
+    from embodiedscan_b200 import MODELS
+    model = MODELS.build(cfg)
+    ref_sd = adjust(fill_state_dict(manifest(g)))
+    ref_sd.update({k[len('calib/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('calib/')})
+    missing, unexpected = model.load_state_dict(ref_sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith('num_batches_tracked') for k in missing), missing
+    return model, {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def rel(a, b):
+    a, b = float(torch.as_tensor(a).detach()), float(torch.as_tensor(b).detach())
+    return abs(a - b) / max(abs(b), 1e-6)
+
+
+WATCH = {'bbox_head.conv_cls.kernel': None, 'bbox_head.conv_reg.kernel': None, 'bbox_head.out_block_0.0.kernel': None,
+         'bbox_head.up_block_1.0.kernel': None, 'backbone_3d.conv1.kernel': None,
+         'backbone_3d.layer2.0.conv1.kernel': None, 'backbone_3d.layer1.0.norm1.bn.weight': None,
+         'backbone.layer2.0.conv1.weight': 'backbone.layer2.0.cb1.conv.weight', 'bbox_head.scales.1.scale': None}
+
+
+def sampled(g):
+    return g if g.numel() <= 4096 else g.flatten()[:: max(g.numel() // 4096, 1)][:4096]
+
+
+@pytest.mark.parametrize('tag,n_scans,augment', [('a', 1, False), ('b', 2, True)])
+def test_detector_loss_and_gradients_match_reference(tag, n_scans, augment):
+    from oracle import model_ref as M
+    g = load('detector_g1')
+    cfg = det_config()
+    _, sd = product_state_dict(cfg, g, adjust_fcaf3d_head)
+    batch = det_inputs(n_scans, augment)
+    assert [len(p) for p in batch['inputs']['points']] == g[f'{tag}_n_points'].tolist()
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    for ref_name, own in WATCH.items():
+        k = own or ref_name
+        sd[k] = sd[k].clone().requires_grad_(True)
+    out = M.detector_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
+    sum(out.values()).backward()
+    for k in ('loss_center', 'loss_bbox', 'loss_cls'):
+        assert rel(out[k], g[f'{tag}_{k}']) <= 2e-5, (k, float(out[k]), float(g[f'{tag}_{k}']))
+    for ref_name, own in WATCH.items():
+        grad = sd[own or ref_name].grad
+        want = torch.from_numpy(g[f'{tag}_grad/{ref_name}'])
+        got = sampled(grad).reshape(want.shape)
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 2e-4 * scale, (ref_name, float((got - want).abs().max()), scale)
+        assert rel(grad.double().norm(), g[f'{tag}_gradnorm/{ref_name}']) <= 5e-4, ref_name   # rotation columns: atan2/asin chains
+
+
+def test_detector_predictions_match_reference():
+    from oracle import model_ref as M
+    g = load('detector_g1')
+    cfg = det_config()
+    cfg['test_cfg'] = dict(nms_pre=50, iou_thr=.5, score_thr=.01)
+    _, sd = product_state_dict(cfg, g, lambda s: adjust_for_predict(adjust_fcaf3d_head(s)))
+    batch = det_inputs(1, False)
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    with torch.no_grad():
+        boxes, scores, labels = M.detector_predict(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])[0]
+    assert len(g['p_labels']) > 10, 'the fixture must exercise NMS'
+    assert torch.equal(labels, torch.from_numpy(g['p_labels'])), 'selection order must be identical'
+    assert float((scores - torch.from_numpy(g['p_scores'])).abs().max()) <= 1e-5
+    want = torch.from_numpy(g['p_boxes'])
+    assert want.shape[1] == 9 and float(want[:, 7:].abs().max()) == 0.0
+    assert float((boxes - want[:, :7]).abs().max()) <= 1e-4 * float(want.abs().max())
