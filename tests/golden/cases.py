@@ -26,3 +26,19 @@ def det_config():
     cfg = mv_det3d_config('C1')
     cfg['backbone_3d']['depth'] = 18                # the reference's MinkResNet has no depth 14 (mink_resnet.py:29-35)
     return cfg
+
+
+def occ_config():
+    from embodiedscan_b200.synth import mv_occ_config
+    cfg = mv_occ_config('C3-small')
+    cfg['backbone_3d']['depth'] = 18
+    return cfg
+
+
+def occ_inputs(seed_scan=1):
+    from embodiedscan_b200.synth import synth_batch, synth_occupancy
+    cfg = occ_config()
+    batch = synth_batch(seed_scan, 1, n_views=2, H=240, W=320, n_points=4000)
+    for ds in batch['data_samples']:
+        ds.gt_occupancy = synth_occupancy(ds, cfg['point_cloud_range'], cfg['n_voxels'])
+    return batch

@@ -28,7 +28,7 @@ import refstubs  # noqa: E402
 
 refstubs.install()
 
-from cases import det_config, det_inputs  # noqa: E402
+from cases import det_config, det_inputs, occ_config, occ_inputs  # noqa: E402
 from weights import adjust_fcaf3d_head, adjust_for_predict, fill_tensor  # noqa: E402
 
 
@@ -92,6 +92,8 @@ def ref_data_samples(data_samples):
                                                  origin=(.5, .5, .5))
         gt.labels_3d = ds.gt_instances_3d.labels_3d.clone()
         r.gt_instances_3d = gt
+        if hasattr(ds, 'gt_occupancy'):
+            r.gt_occupancy = ds.gt_occupancy.clone()
         out.append(r)
     return out
 
@@ -148,9 +150,21 @@ def gen_detector():
     model.load_state_dict(sd)
     model.bbox_head.test_cfg.nms_pre = 50
     model.eval()
-    with torch.no_grad():
-        res = model(dict(points=batch['inputs']['points'], imgs=imgs), ref_data_samples(batch['data_samples']),
-                    mode='predict')
+
+    def run(thr):
+        model.bbox_head.test_cfg.score_thr = thr
+        with torch.no_grad():
+            return model(dict(points=batch['inputs']['points'], imgs=imgs), ref_data_samples(batch['data_samples']),
+                         mode='predict')
+    # score threshold = middle of the widest gap between neighbouring scores near the configured 0.01, so that fp32
+    # noise on the CUDA side cannot move a detection across it
+    sc = np.sort(_np(run(0.005)[0].pred_instances_3d.scores_3d))
+    sc = sc[(sc > 0.008) & (sc < 0.02)]
+    i = int(np.argmax(np.diff(sc)))
+    thr = float(np.float32((sc[i] + sc[i + 1]) / 2))
+    print('score_thr', thr, 'gap', float(sc[i + 1] - sc[i]))
+    out['p_score_thr'] = np.float32(thr)
+    res = run(thr)
     pred = res[0].pred_instances_3d
     out['p_boxes'], out['p_scores'], out['p_labels'] = pred.bboxes_3d.tensor, pred.scores_3d, pred.labels_3d
     print('detector: losses', {k: float(v.detach()) for k, v in out.items() if k.startswith(('a_loss', 'b_loss'))},
@@ -158,7 +172,61 @@ def gen_detector():
     save('detector_g1', **out)
 
 
-GENERATORS = dict(detector=gen_detector)
+OCC_WATCH = ('bbox_head.occ.0.weight', 'bbox_head.occ.2.weight', 'neck_3d.down_layer_1.0.conv1.weight',
+             'neck_3d.up_block_1.0.weight', 'neck.lateral_convs.0.conv.weight', 'neck.lateral_convs.3.conv.bias',
+             'backbone_3d.layer4.0.conv1.kernel', 'backbone_3d.conv1.kernel', 'backbone.layer2.0.conv1.weight')
+
+
+# scan 5: no ReLU pre-activation of the 4-voxel coarse level sits within fp32 noise of zero (scans 1, 3, 4 each have one
+# such unit, and one flipped mask moves single gradient entries by percents - a fixture artefact, not a semantic one)
+OCC_TRAIN_SCAN = int(os.environ.get('OCC_TRAIN_SCAN', 5))
+
+
+def gen_occupancy():
+    from oracle import model_ref as M
+    cfg = occ_config()
+    model = build_reference_detector(cfg)
+    manifest = fill_module(model)
+    out = manifest_arrays(manifest)
+
+    def inputs(seed_scan):
+        batch = occ_inputs(seed_scan)
+        imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                                 cfg['data_preprocessor']['std'])
+        return dict(points=batch['inputs']['points'], imgs=imgs), ref_data_samples(batch['data_samples'])
+    cal_in, cal_ds = inputs(1)
+    calib = calibrate_norms(model, lambda: model(cal_in, cal_ds, mode='loss'))
+    out.update(calib)
+    model.train()
+    x, ds = inputs(OCC_TRAIN_SCAN)
+    losses = model(x, ds, mode='loss')
+    sum(losses.values()).backward()
+    for k, v in losses.items():
+        out['a_' + k] = v
+    out['a_scan'] = np.int64(OCC_TRAIN_SCAN)
+    params = dict(model.named_parameters())
+    for k in OCC_WATCH:
+        g = params[k].grad
+        out[f'a_grad/{k}'] = g if g.numel() <= 4096 else g.flatten()[:: max(g.numel() // 4096, 1)][:4096]
+        out[f'a_gradnorm/{k}'] = g.double().norm()
+    sd = {k: fill_tensor(k, sh) for k, sh in manifest}
+    sd.update({k[len('calib/'):]: v for k, v in calib.items()})
+    model.load_state_dict(sd)
+    model.eval()
+    x, ds = inputs(2)
+    with torch.no_grad():
+        res = model(x, ds, mode='predict')
+        feats, _ = model.extract_feat(x, ds)
+        logits = model.bbox_head(feats, None)[0]
+    out['p_occupancy'] = res[0].pred_occupancy
+    top2 = torch.topk(torch.softmax(logits, 1), 2, dim=1).values
+    out['p_margin'] = (top2[:, 0] - top2[:, 1])[0]            # how decisive each voxel's argmax is
+    print('occupancy: losses', {k: float(v.detach()) for k, v in losses.items()}, 'pred classes',
+          torch.unique(res[0].pred_occupancy).numel(), 'min margin', float(out['p_margin'].min()))
+    save('occupancy_g3', **out)
+
+
+GENERATORS = dict(detector=gen_detector, occupancy=gen_occupancy)
 
 if __name__ == '__main__':
     torch.manual_seed(0)

@@ -110,13 +110,13 @@ class SparseTensor:
         """(B, C, X, Y, Z) dense tensor; coordinates are shifted by `min_coordinate` and divided by the tensor stride."""
         mn = min_coordinate.view(-1).numpy().astype(np.int64) if min_coordinate is not None else np.zeros(3, np.int64)
         idx = (self._coords[:, 1:] - mn[None]) // self._stride
-        out = self.F.new_zeros(tuple(shape))
-        ok = ((idx >= 0) & (idx < np.asarray(shape[2:])[None])).all(1)
+        B, C, X, Y, Z = tuple(shape)
+        ok = ((idx >= 0) & (idx < np.asarray([X, Y, Z])[None])).all(1)
         rows = torch.from_numpy(np.nonzero(ok)[0])
         b = torch.from_numpy(self._coords[ok, 0])
         i = torch.from_numpy(idx[ok])
-        out = out.index_put((b, slice(None), i[:, 0], i[:, 1], i[:, 2]), self.F[rows])
-        return out, torch.from_numpy(mn), torch.tensor(self.tensor_stride)
+        out = self.F.new_zeros((B, X, Y, Z, C)).index_put((b, i[:, 0], i[:, 1], i[:, 2]), self.F[rows])
+        return out.permute(0, 4, 1, 2, 3), torch.from_numpy(mn), torch.tensor(self.tensor_stride)
 
 
 def cat(a, b):

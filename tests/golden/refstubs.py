@@ -270,6 +270,20 @@ def _install_mmcv():
     cnn = _mod('mmcv.cnn')
     cnn.Scale = Scale
     cnn.Linear = nn.Linear
+
+    def build_conv_layer(cfg, *args, **kwargs):
+        cfg = dict(cfg or dict(type='Conv2d'))
+        layer = {'Conv1d': nn.Conv1d, 'Conv2d': nn.Conv2d, 'Conv3d': nn.Conv3d, 'Conv': nn.Conv2d}[cfg.pop('type')]
+        return layer(*args, **kwargs, **cfg)
+    cnn.build_conv_layer = build_conv_layer
+
+    def build_norm_layer(cfg, num_features, postfix=''):
+        cfg = dict(cfg)
+        t = cfg.pop('type')
+        cfg.pop('requires_grad', None)
+        layer = {'BN': nn.BatchNorm2d, 'BN1d': nn.BatchNorm1d, 'BN3d': nn.BatchNorm3d, 'LN': nn.LayerNorm}[t]
+        return t.lower() + str(postfix), layer(num_features, **cfg)
+    cnn.build_norm_layer = build_norm_layer
     _mod('mmcv.cnn.bricks')
     _mod('mmcv.cnn.bricks.transformer')
     _mod('mmcv.utils').ext_loader = _Dummy()

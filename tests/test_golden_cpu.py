@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import det_config, det_inputs  # noqa: E402
+from cases import det_config, det_inputs, occ_config, occ_inputs  # noqa: E402
 from weights import adjust_fcaf3d_head, adjust_for_predict, fill_state_dict  # noqa: E402
 
 
@@ -86,7 +86,7 @@ def test_detector_predictions_match_reference():
     from oracle import model_ref as M
     g = load('detector_g1')
     cfg = det_config()
-    cfg['test_cfg'] = dict(nms_pre=50, iou_thr=.5, score_thr=.01)
+    cfg['test_cfg'] = dict(nms_pre=50, iou_thr=.5, score_thr=float(g['p_score_thr']))
     _, sd = product_state_dict(cfg, g, lambda s: adjust_for_predict(adjust_fcaf3d_head(s)))
     batch = det_inputs(1, False)
     imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
@@ -99,3 +99,58 @@ def test_detector_predictions_match_reference():
     want = torch.from_numpy(g['p_boxes'])
     assert want.shape[1] == 9 and float(want[:, 7:].abs().max()) == 0.0
     assert float((boxes - want[:, :7]).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ occupancy (a14)
+OCC_WATCH = {'bbox_head.occ.0.weight': None, 'bbox_head.occ.2.weight': None, 'neck_3d.down_layer_1.0.conv1.weight': None,
+             'neck_3d.up_block_1.0.weight': None, 'neck.lateral_convs.0.conv.weight': None,
+             'neck.lateral_convs.3.conv.bias': None, 'backbone_3d.layer4.0.conv1.kernel': None,
+             'backbone_3d.conv1.kernel': None, 'backbone.layer2.0.conv1.weight': 'backbone.layer2.0.cb1.conv.weight'}
+
+
+def test_occupancy_loss_and_gradients_match_reference():
+    from oracle import model_ref as M
+    from oracle import occ_ref as R
+    g = load('occupancy_g3')
+    cfg = occ_config()
+    _, sd = product_state_dict(cfg, g, lambda s: s)
+    batch = occ_inputs(int(g['a_scan']))
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    for ref_name, own in OCC_WATCH.items():
+        k = own or ref_name
+        sd[k] = sd[k].clone().requires_grad_(True)
+    out = R.occ_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
+    sum(out.values()).backward()
+    for k in ('loss_occ_0', 'loss_occ_1', 'loss_occ_2'):
+        assert rel(out[k], g['a_' + k]) <= 2e-5, (k, float(out[k]), float(g['a_' + k]))
+    for ref_name, own in OCC_WATCH.items():
+        grad = sd[own or ref_name].grad
+        want = torch.from_numpy(g[f'a_grad/{ref_name}'])
+        got = sampled(grad).reshape(want.shape)
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 2e-4 * scale, (ref_name, float((got - want).abs().max()), scale)
+        assert rel(grad.double().norm(), g[f'a_gradnorm/{ref_name}']) <= 2e-4, ref_name
+
+
+def check_occupancy_prediction(pred, g, decisive_margin=1e-3):
+    want, margin = torch.from_numpy(g['p_occupancy']), torch.from_numpy(g['p_margin'])
+    assert pred.shape == want.shape
+    decisive = margin > decisive_margin          # near-tied argmax voxels may flip under fp32 reordering
+    assert int(decisive.sum()) > 0.5 * decisive.numel()
+    assert torch.equal(pred[decisive], want[decisive])
+    assert float((pred == want).float().mean()) >= 0.99
+
+
+def test_occupancy_predictions_match_reference():
+    from oracle import model_ref as M
+    from oracle import occ_ref as R
+    g = load('occupancy_g3')
+    cfg = occ_config()
+    _, sd = product_state_dict(cfg, g, lambda s: s)
+    batch = occ_inputs(2)
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    with torch.no_grad():
+        pred = R.occ_predict(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])[0]
+    check_occupancy_prediction(pred, g)
