@@ -48,29 +48,37 @@ class Det3DDataPreprocessor(nn.Module):
             out['points'] = [p.to(dev, non_blocking=True) for p in inputs['points']]
         if 'img' in inputs:
             imgs = inputs['img']
-            if isinstance(imgs, (list, tuple)):
-                shapes = {tuple(i.shape) for i in imgs}
-                assert len(shapes) == 1, 'views of a batch share one shape on the hot path'
-                imgs = torch.stack([i.to(dev, non_blocking=True) for i in imgs])
-            else:
+            if isinstance(imgs, torch.Tensor):                      # default_collate: one (B,[V,]3,H,W) tensor, one copy
                 imgs = imgs.to(dev, non_blocking=True)
-            if imgs.dim() == 4:
-                imgs = imgs[:, None]
-            assert imgs.dtype == torch.uint8, 'images arrive as uint8 CHW (Pack3DDetInputs)'
-            B, V, C, H, W = imgs.shape
+                imgs = list(imgs[:, None] if imgs.dim() == 4 else imgs)
+            imgs = [i[None] if i.dim() == 3 else i for i in imgs]   # (V,3,H,W) per scan
+            assert all(i.dtype == torch.uint8 for i in imgs), 'images arrive as uint8 CHW (Pack3DDetInputs)'
+            assert len({i.shape[0] for i in imgs}) == 1, 'scans of a batch carry the same number of views'
+            assert self.pad_value == 0, 'the pad region is written as 0 in normalised space (configs use pad_value=0)'
+            B, V = len(imgs), imgs[0].shape[0]
             d = self.pad_size_divisor
-            Hp, Wp = int(math.ceil(H / d) * d), int(math.ceil(W / d) * d)
+            # multiview_img_stack_batch (utils.py:9-63): every scan is right/bottom padded to the batch maximum,
+            # rounded up to the divisor; `pad_shape` stays per scan (data_preprocessor.py:_get_pad_shape)
+            Hp = int(math.ceil(max(i.shape[-2] for i in imgs) / d) * d)
+            Wp = int(math.ceil(max(i.shape[-1] for i in imgs) / d) * d)
             buf = torch.empty((B * V, Hp, Wp, 3), dtype=self.compute_dtype, device=dev)
             import ctypes
             mean = (ctypes.c_float * 3)(*self.mean)
             std = (ctypes.c_float * 3)(*self.std)
-            call('esb_img_normalize', ptr(imgs.contiguous()), B * V, H, W, Hp, Wp, ctypes.cast(mean, ctypes.c_void_p),
-                 ctypes.cast(std, ctypes.c_void_p), 1 if self.channel_conversion else 0, 1, ptr(buf),
-                 _ffi.dtype_code(self.compute_dtype), stream())
+            uniform = len({tuple(i.shape) for i in imgs}) == 1
+            groups = [(torch.stack([i.to(dev, non_blocking=True) for i in imgs]), buf)] if uniform else \
+                [(i.to(dev, non_blocking=True), buf[b * V:(b + 1) * V]) for b, i in enumerate(imgs)]
+            for src, dst in groups:                                 # one launch for the usual uniform batch
+                H, W = src.shape[-2:]
+                call('esb_img_normalize', ptr(src.contiguous()), dst.shape[0], H, W, Hp, Wp,
+                     ctypes.cast(mean, ctypes.c_void_p), ctypes.cast(std, ctypes.c_void_p),
+                     1 if self.channel_conversion else 0, 1, ptr(dst), _ffi.dtype_code(self.compute_dtype), stream())
             out['imgs'] = buf.view(B, V, Hp, Wp, 3).permute(0, 1, 4, 2, 3)   # (B,V,3,Hp,Wp), channels-last memory
             if data_samples is not None:
-                for ds in data_samples:
-                    ds.set_metainfo({'batch_input_shape': (Hp, Wp), 'pad_shape': (Hp, Wp)})
+                for ds, i in zip(data_samples, imgs):
+                    ds.set_metainfo({'batch_input_shape': (Hp, Wp),
+                                     'pad_shape': (int(math.ceil(i.shape[-2] / d) * d),
+                                                   int(math.ceil(i.shape[-1] / d) * d))})
         elif 'imgs' in inputs:
             out['imgs'] = inputs['imgs'].to(dev)
         if data_samples is not None:

@@ -42,3 +42,18 @@ def occ_inputs(seed_scan=1):
     for ds in batch['data_samples']:
         ds.gt_occupancy = synth_occupancy(ds, cfg['point_cloud_range'], cfg['n_voxels'])
     return batch
+
+
+def preprocess_inputs():
+    """Two scans x two views of different sizes: exercises BGR->RGB, normalisation and the multi-view pad-to-max."""
+    g = torch.Generator().manual_seed(77)
+    return [torch.randint(0, 256, (2, 3, 30, 45), generator=g, dtype=torch.uint8),
+            torch.randint(0, 256, (2, 3, 33, 40), generator=g, dtype=torch.uint8)]
+
+
+def unproject_inputs():
+    """V=3 small depth maps in uint16 millimetres (7 % zero pixels) with the synthetic cameras of scan 11."""
+    from embodiedscan_b200.synth import synth_scan
+    s = synth_scan(11, n_views=3, H=24, W=32, n_points=64)
+    meta = s['data_sample'].metainfo
+    return s['depth'], meta['depth2img']['intrinsic'], meta['depth2img']['extrinsic']

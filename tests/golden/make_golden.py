@@ -28,7 +28,8 @@ import refstubs  # noqa: E402
 
 refstubs.install()
 
-from cases import det_config, det_inputs, occ_config, occ_inputs  # noqa: E402
+from cases import (det_config, det_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
+                   unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, fill_tensor  # noqa: E402
 
 
@@ -226,7 +227,36 @@ def gen_occupancy():
     save('occupancy_g3', **out)
 
 
-GENERATORS = dict(detector=gen_detector, occupancy=gen_occupancy)
+def gen_frontend():
+    """a1: Det3DDataPreprocessor.collate_data (data_preprocessor.py:249-339 + utils.py:9-63).
+    a2: LoadDepthFromFile's `/ depth_shift` (loading.py:70-73) -> ConvertRGBDToPoints.transform (points.py:30-81) ->
+    AggregateMultiViewPoints.transform (multiview.py:139-169)."""
+    from embodiedscan.datasets.transforms.multiview import AggregateMultiViewPoints
+    from embodiedscan.datasets.transforms.points import ConvertRGBDToPoints
+    from embodiedscan.models.data_preprocessors.data_preprocessor import Det3DDataPreprocessor
+    out = {}
+    pre = Det3DDataPreprocessor(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], bgr_to_rgb=True,
+                                pad_size_divisor=32)
+    imgs = preprocess_inputs()
+    data = dict(inputs=dict(img=[i.clone() for i in imgs]), data_samples=None)
+    out['pre_imgs'] = pre.collate_data(data)['inputs']['imgs']
+    out['pre_pad_shape'] = np.array(pre._get_pad_shape(dict(inputs=dict(img=imgs))))
+
+    depth, intr, extr = unproject_inputs()
+    conv, agg = ConvertRGBDToPoints(coord_type='DEPTH'), AggregateMultiViewPoints(coord_type='DEPTH')
+    per_view = []
+    for v in range(depth.shape[0]):
+        d = depth[v].numpy().astype(np.float32) / 1000.0
+        per_view.append(conv.transform(dict(depth_img=d, depth_cam2img=intr[v]))['points'])
+    out['unproj_counts'] = np.array([len(p.tensor) for p in per_view])
+    res = agg.transform(dict(points=per_view, depth2img=dict(extrinsic=[np.asarray(e) for e in extr])))
+    out['unproj_points'] = res['points'].tensor
+    print('frontend: imgs', tuple(out['pre_imgs'].shape), 'pad', out['pre_pad_shape'].tolist(), 'points',
+          tuple(out['unproj_points'].shape))
+    save('frontend', **out)
+
+
+GENERATORS = dict(detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend)
 
 if __name__ == '__main__':
     torch.manual_seed(0)

@@ -482,7 +482,29 @@ class CrossEntropyLoss(nn.Module):
         return self.loss_weight * _weight_reduce(loss, weight, reduction_override or self.reduction, avg_factor)
 
 
+class DetDataPreprocessor(nn.Module):
+    """mmdet.DetDataPreprocessor / mmengine.ImgDataPreprocessor: only the state the reference subclass reads
+    (`mean`/`std` buffers of shape (3,1,1), `_channel_conversion`, `_enable_normalize`, pad settings, `cast_data`)."""
+
+    def __init__(self, mean=None, std=None, pad_size_divisor=1, pad_value=0, pad_mask=False, mask_pad_value=0,
+                 pad_seg=False, seg_pad_value=255, bgr_to_rgb=False, rgb_to_bgr=False, boxtype2tensor=True,
+                 non_blocking=False, batch_augments=None):
+        super().__init__()
+        assert not (bgr_to_rgb and rgb_to_bgr)
+        self._channel_conversion = rgb_to_bgr or bgr_to_rgb
+        self._enable_normalize = mean is not None
+        if mean is not None:
+            self.register_buffer('mean', torch.tensor(mean, dtype=torch.float32).view(-1, 1, 1), False)
+            self.register_buffer('std', torch.tensor(std, dtype=torch.float32).view(-1, 1, 1), False)
+        self.pad_size_divisor, self.pad_value = pad_size_divisor, pad_value
+        self.pad_mask, self.pad_seg, self.boxtype2tensor, self.batch_augments = pad_mask, pad_seg, False, batch_augments
+
+    def cast_data(self, data):
+        return data
+
+
 def _install_mmdet_models():
+    sys.modules['mmdet.models'].DetDataPreprocessor = DetDataPreprocessor
     reg = sys.modules['mmengine'].MODELS
     for cls in (ResNet, FPN, FocalLoss, CrossEntropyLoss):
         reg.register_module(module=cls)

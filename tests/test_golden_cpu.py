@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import det_config, det_inputs, occ_config, occ_inputs  # noqa: E402
+from cases import det_config, det_inputs, occ_config, occ_inputs, preprocess_inputs, unproject_inputs  # noqa: E402
 from weights import adjust_fcaf3d_head, adjust_for_predict, fill_state_dict  # noqa: E402
 
 
@@ -154,3 +154,31 @@ def test_occupancy_predictions_match_reference():
     with torch.no_grad():
         pred = R.occ_predict(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])[0]
     check_occupancy_prediction(pred, g)
+
+
+# ------------------------------------------------------------------------------------------------ front-end (a1, a2)
+MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+
+
+def test_image_collation_matches_reference():
+    from oracle import data_ref as D
+    g = load('frontend')
+    imgs = preprocess_inputs()
+    out = D.preprocess_multiview(imgs, MEAN, STD, True, 32)
+    assert torch.equal(out, torch.from_numpy(g['pre_imgs'])), 'fp32 (x-mean)/std and zero padding are exact'
+    assert D.pad_shapes(imgs, 32) == [tuple(r) for r in g['pre_pad_shape'].tolist()]
+    # the uniform-shape helper used by the model-level oracle agrees with it
+    from oracle import model_ref as M
+    same = [imgs[0], imgs[0].flip(0)]
+    assert torch.equal(M.preprocess_imgs(torch.stack(same), MEAN, STD), D.preprocess_multiview(same, MEAN, STD))
+
+
+def test_unprojection_matches_reference():
+    from oracle import data_ref as D
+    g = load('frontend')
+    depth, intr, extr = unproject_inputs()
+    pts, counts = D.unproject_depth(depth, intr, extr)
+    assert counts.tolist() == g['unproj_counts'].tolist()
+    assert int((depth == 0).sum()) > 0, 'the fixture must contain dropped pixels'
+    want = torch.from_numpy(g['unproj_points'])
+    assert float((pts - want).abs().max()) <= 1e-6 * float(want.abs().max())

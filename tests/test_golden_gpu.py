@@ -6,7 +6,7 @@ Bar (BASELINE.json north_star): selection order / labels identical, fp32 values 
 import pytest
 import torch
 
-from test_golden_cpu import (OCC_WATCH, WATCH, check_occupancy_prediction, occ_config, occ_inputs, adjust_fcaf3d_head, adjust_for_predict, det_config, det_inputs, load,
+from test_golden_cpu import (MEAN, OCC_WATCH, STD, WATCH, preprocess_inputs, unproject_inputs, check_occupancy_prediction, occ_config, occ_inputs, adjust_fcaf3d_head, adjust_for_predict, det_config, det_inputs, load,
                              product_state_dict, rel, sampled)
 
 pytestmark = pytest.mark.gpu
@@ -93,3 +93,28 @@ def test_occupancy_predictions_match_reference():
     with torch.no_grad():
         out = model.val_step(dict(inputs=batch['inputs'], data_samples=batch['data_samples']))
     check_occupancy_prediction(out[0].pred_occupancy.cpu(), g, decisive_margin=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ front-end (a1, a2)
+def test_image_collation_matches_reference():
+    from embodiedscan_b200.detectors import Det3DDataPreprocessor
+    from embodiedscan_b200.structures import Det3DDataSample
+    g = load('frontend')
+    pre = Det3DDataPreprocessor(mean=MEAN, std=STD, bgr_to_rgb=True, pad_size_divisor=32).to(DEV)
+    samples = [Det3DDataSample(metainfo={}), Det3DDataSample(metainfo={})]
+    out = pre(dict(inputs=dict(img=preprocess_inputs()), data_samples=samples))
+    assert torch.equal(out['inputs']['imgs'].cpu(), torch.from_numpy(g['pre_imgs'])), \
+        'one rounded fp32 sub and div per pixel, zeros in the pad region: exact'
+    assert [tuple(s.metainfo['pad_shape']) for s in samples] == [tuple(r) for r in g['pre_pad_shape'].tolist()]
+    assert all(tuple(s.metainfo['batch_input_shape']) == (64, 64) for s in samples)
+
+
+def test_unprojection_matches_reference():
+    from embodiedscan_b200.transforms import unproject_multiview
+    g = load('frontend')
+    depth, intr, extr = unproject_inputs()
+    pts, view = unproject_multiview(depth.to(DEV), intr, extr, return_view=True)
+    assert torch.bincount(view.cpu().long(), minlength=depth.shape[0]).tolist() == g['unproj_counts'].tolist()
+    want = torch.from_numpy(g['unproj_points'])
+    # one composed fp32 4x4 per pixel vs the reference's fp32 inverse + fp32 solve: a few ulp of the coordinate range
+    assert float((pts.cpu() - want).abs().max()) <= 1e-5 * float(want.abs().max())
