@@ -57,3 +57,42 @@ def unproject_inputs():
     s = synth_scan(11, n_views=3, H=24, W=32, n_points=64)
     meta = s['data_sample'].metainfo
     return s['depth'], meta['depth2img']['intrinsic'], meta['depth2img']['extrinsic']
+
+
+def fusion_inputs():
+    """Point painting with every branch of the reversed augmentation flow switched on (HF, VF, R, S, T), an image flip,
+    non-unit scale factors and a crop offset; features small enough for an exact element-wise comparison."""
+    import math
+    from embodiedscan_b200.synth import synth_scan
+    s = synth_scan(21, n_views=3, H=60, W=90, n_points=400)
+    g = torch.Generator().manual_seed(5)
+    meta = dict(s['data_sample'].metainfo)
+    ang = 0.07
+    rot = torch.tensor([[math.cos(ang), -math.sin(ang), 0.], [math.sin(ang), math.cos(ang), 0.], [0., 0., 1.]]).t()
+    meta.update(transformation_3d_flow=['HF', 'VF', 'R', 'S', 'T'], pcd_horizontal_flip=True, pcd_vertical_flip=True,
+                pcd_rotation=rot.contiguous().numpy(), pcd_scale_factor=1.07,
+                pcd_trans=np.array([0.11, -0.07, 0.03], dtype=np.float32), flip=True, scale_factor=(0.9, 1.1),
+                img_crop_offset=(3.0, 5.0), img_shape=(60, 90))
+    # points as the model sees them: augmented copies of the scan points (flip . rotate . scale . translate)
+    # jitter: scan points are unprojected pixel centres, so they re-project onto exact half-pixel ties of the feature
+    # grid (ix = 11.5), where nearest rounding is decided by the last ulp; real inputs are voxel centres, not pixel rays
+    p = s['points'].clone() + 0.004 * torch.randn(s['points'].shape, generator=g)
+    p[:, 0] = -p[:, 0]
+    p[:, 1] = -p[:, 1]
+    p = (p @ rot) * 1.07 + torch.tensor([0.11, -0.07, 0.03])
+    feats = torch.randn(3, 8, 16, 24, generator=g)
+    return meta, feats, p.contiguous(), (64, 96)
+
+
+def target_cases():
+    """(points per level, boxes (n,9), labels) triples for FCAF3D target assignment edge cases."""
+    g = torch.Generator().manual_seed(9)
+    lv = [torch.rand(n, 3, generator=g) * torch.tensor([4., 4., 2.]) - torch.tensor([2., 2., 0.])
+          for n in (600, 150, 40, 10)]
+    boxes = torch.tensor([[0.0, 0.0, 1.0, 2.0, 1.5, 1.2, 0.4, 0.05, -0.03],
+                          [0.5, -0.5, 0.8, 0.8, 0.9, 0.7, -1.1, 0.0, 0.02],      # nested in the first: min-volume rule
+                          [-1.2, 1.1, 0.5, 0.5, 0.4, 0.6, 2.0, 0.0, 0.0],
+                          [5.0, 5.0, 5.0, 0.3, 0.3, 0.3, 0.0, 0.0, 0.0]])       # contains no point at all
+    labels = torch.tensor([7, 200, 31, 5])
+    few = [torch.rand(n, 3, generator=g) - 0.5 + torch.tensor([0., 0., 1.]) for n in (6, 3, 2, 1)]  # < 19 points
+    return dict(regular=(lv, boxes, labels), empty_gt=(lv, boxes[:0], labels[:0]), few_points=(few, boxes[:2], labels[:2]))

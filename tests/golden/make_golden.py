@@ -28,8 +28,8 @@ import refstubs  # noqa: E402
 
 refstubs.install()
 
-from cases import (det_config, det_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
-                   unproject_inputs)
+from cases import (det_config, det_inputs, fusion_inputs, occ_config, occ_inputs,  # noqa: E402
+                   preprocess_inputs, target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, fill_tensor  # noqa: E402
 
 
@@ -256,7 +256,45 @@ def gen_frontend():
     save('frontend', **out)
 
 
-GENERATORS = dict(detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend)
+def gen_functions():
+    """Function-level pins with the branches the model-level fixtures do not reach."""
+    from embodiedscan.models.dense_heads.fcaf3d_head import FCAF3DHeadRotMat
+    from embodiedscan.models.layers.fusion_layers.point_fusion import batch_point_sample
+    from embodiedscan.structures import EulerDepthInstance3DBoxes
+    from mmengine import ConfigDict
+    out = {}
+    # a6: point_fusion.py:20-107,208-311 with HF/VF/R/S/T reversed, image flip, scale factors, crop offset
+    meta, feats, pts, pad_hw = fusion_inputs()
+    pm = meta['depth2img']
+    proj = torch.stack([torch.tensor(pm['intrinsic'][v]) @ torch.tensor(pm['extrinsic'][v])
+                        for v in range(feats.shape[0])])
+    out['fusion_out'] = batch_point_sample(meta, img_features=feats, points=pts, proj_mat=proj, coord_type='DEPTH',
+                                           img_scale_factor=torch.tensor(meta['scale_factor'][:2]),
+                                           img_crop_offset=torch.tensor(meta['img_crop_offset']),
+                                           img_flip=meta['flip'], img_pad_shape=pad_hw,
+                                           img_shape=meta['img_shape'][:2], aligned=False)
+    print('fusion: painted rows', int((out['fusion_out'].abs().sum(1) > 0).sum()), 'of', len(pts))
+    # a9: fcaf3d_head.py:1578-1664 edge cases (nested boxes, a box without points, no GT, fewer points than top-k)
+    head = FCAF3DHeadRotMat(num_classes=284, in_channels=(8, 16, 32, 64), out_channels=8, num_reg_outs=12,
+                            voxel_size=.01, pts_prune_threshold=1000, pts_assign_threshold=27,
+                            pts_center_threshold=18, decouple_bbox_loss=True, decouple_groups=4,
+                            decouple_weights=[0.2, 0.2, 0.2, 0.4], test_cfg=ConfigDict(nms_pre=1000, iou_thr=.5,
+                                                                                       score_thr=.01))
+    for name, (lv, boxes, labels) in target_cases().items():
+        gt = EulerDepthInstance3DBoxes(boxes.clone(), box_dim=9, origin=(.5, .5, .5))
+        c, b, k = head.get_targets([p.clone() for p in lv], gt, labels)
+        out[f'targets_{name}_center'], out[f'targets_{name}_bbox'], out[f'targets_{name}_cls'] = c, b, k
+        print('targets', name, 'positives', int((k >= 0).sum()))
+    # a11: no class clears the threshold -> empty, 7-column result (fcaf3d_head.py:1709-1724)
+    b, s_, l = head._single_scene_multiclass_nms(torch.rand(5, 9), torch.full((5, 284), 0.001), {})
+    out['nms_empty_shapes'] = np.array([*b.shape, *s_.shape, *l.shape])
+    # a12: euler_box3d.py:137-184 corner order and rotation
+    boxes = target_cases()['regular'][1]
+    out['corners'] = EulerDepthInstance3DBoxes(boxes.clone(), box_dim=9, origin=(.5, .5, .5)).corners
+    save('functions', **out)
+
+
+GENERATORS = dict(detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions)
 
 if __name__ == '__main__':
     torch.manual_seed(0)

@@ -15,7 +15,8 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import det_config, det_inputs, occ_config, occ_inputs, preprocess_inputs, unproject_inputs  # noqa: E402
+from cases import (det_config, det_inputs, fusion_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
+                   target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, fill_state_dict  # noqa: E402
 
 
@@ -182,3 +183,47 @@ def test_unprojection_matches_reference():
     assert int((depth == 0).sum()) > 0, 'the fixture must contain dropped pixels'
     want = torch.from_numpy(g['unproj_points'])
     assert float((pts - want).abs().max()) <= 1e-6 * float(want.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ function-level pins
+def test_point_painting_all_branches_matches_reference():
+    from oracle import model_ref as M
+    g = load('functions')
+    meta, feats, pts, pad_hw = fusion_inputs()
+    pm = meta['depth2img']
+    proj = torch.from_numpy(np.stack([M.compose_projection(pm['intrinsic'][v], pm['extrinsic'][v])
+                                      for v in range(feats.shape[0])]))
+    out, valid = M.batch_point_sample(meta, feats, pts, proj, pad_hw)
+    want = torch.from_numpy(g['fusion_out'])
+    assert int((valid > 0).sum()) > 100 and int((valid == 0).sum()) > 0
+    # nearest-pixel selection must be identical: a wrong pixel changes a row by O(1), round-off by O(1e-7)
+    assert float((out - want).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize('name', ['regular', 'empty_gt', 'few_points'])
+def test_target_assignment_edge_cases_match_reference(name):
+    from oracle import model_ref as M
+    g = load('functions')
+    lv, boxes, labels = target_cases()[name]
+    c, b, k = M.get_targets(lv, boxes, labels)
+    assert torch.equal(k, torch.from_numpy(g[f'targets_{name}_cls'])), 'assignment is integer-exact'
+    assert float((c - torch.from_numpy(g[f'targets_{name}_center'])).abs().max()) <= 1e-5     # sqrt of a ratio product
+    assert torch.equal(b, torch.from_numpy(g[f'targets_{name}_bbox']))
+
+
+def test_box_corners_and_empty_nms_match_reference():
+    from oracle import geometry_ref as G
+    g = load('functions')
+    boxes = target_cases()['regular'][1]
+    assert float((G.container_corners(boxes) - torch.from_numpy(g['corners'])).abs().max()) <= 1e-6
+    b, s_, l = G.multiclass_nms(torch.rand(5, 9)[:, :7], torch.full((5, 284), 0.001), 0.01, 0.5)
+    assert [*b.shape, *s_.shape, *l.shape] == g['nms_empty_shapes'].tolist()
+
+
+def test_product_box_container_matches_reference():
+    """Host-side structures of the product (no CUDA involved): corners order / rotation of the 9-DoF box container."""
+    from embodiedscan_b200.structures import EulerDepthInstance3DBoxes
+    g = load('functions')
+    boxes = target_cases()['regular'][1]
+    c = EulerDepthInstance3DBoxes(boxes.clone(), box_dim=9, origin=(.5, .5, .5)).corners
+    assert float((c - torch.from_numpy(g['corners'])).abs().max()) <= 1e-6

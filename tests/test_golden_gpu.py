@@ -6,7 +6,7 @@ Bar (BASELINE.json north_star): selection order / labels identical, fp32 values 
 import pytest
 import torch
 
-from test_golden_cpu import (MEAN, OCC_WATCH, STD, WATCH, preprocess_inputs, unproject_inputs, check_occupancy_prediction, occ_config, occ_inputs, adjust_fcaf3d_head, adjust_for_predict, det_config, det_inputs, load,
+from test_golden_cpu import (MEAN, fusion_inputs, target_cases, OCC_WATCH, STD, WATCH, preprocess_inputs, unproject_inputs, check_occupancy_prediction, occ_config, occ_inputs, adjust_fcaf3d_head, adjust_for_predict, det_config, det_inputs, load,
                              product_state_dict, rel, sampled)
 
 pytestmark = pytest.mark.gpu
@@ -118,3 +118,32 @@ def test_unprojection_matches_reference():
     want = torch.from_numpy(g['unproj_points'])
     # one composed fp32 4x4 per pixel vs the reference's fp32 inverse + fp32 solve: a few ulp of the coordinate range
     assert float((pts.cpu() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ function-level pins
+def test_point_painting_all_branches_matches_reference():
+    """HF + VF + R + S + T reversed, image flip, scale factors, crop offset (point_fusion.py:20-107, 208-311)."""
+    from embodiedscan_b200.fusion import pack_paint_metas, pack_projections, paint_float_points
+    g = load('functions')
+    meta, feats, pts, pad_hw = fusion_inputs()
+    V = feats.shape[0]
+    fd = feats.to(DEV).contiguous(memory_format=torch.channels_last)
+    out = paint_float_points(fd, pts.to(DEV), None, pack_paint_metas([meta], DEV), pack_projections([meta], 'DEPTH', DEV),
+                             pad_hw, V)
+    want = torch.from_numpy(g['fusion_out'])
+    assert int((want.abs().sum(1) > 0).sum()) > 100
+    # a wrong nearest pixel changes a row by O(1); identical selection leaves summation-order noise only
+    assert float((out.cpu() - want).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize('name', ['regular', 'empty_gt', 'few_points'])
+def test_target_assignment_edge_cases_match_reference(name):
+    from embodiedscan_b200.dense_heads import fcaf3d_targets
+    g = load('functions')
+    lv, boxes, labels = target_cases()[name]
+    c, b, k = fcaf3d_targets([p.to(DEV) for p in lv], boxes.to(DEV), labels.to(DEV), 27, 18)
+    want_k = torch.from_numpy(g[f'targets_{name}_cls'])
+    assert torch.equal(k.cpu(), want_k), 'assignment is integer-exact'
+    pos = want_k >= 0
+    assert torch.equal(b.cpu()[pos], torch.from_numpy(g[f'targets_{name}_bbox'])[pos])
+    assert float((c.cpu()[pos] - torch.from_numpy(g[f'targets_{name}_center'])[pos]).abs().max() if pos.any() else 0.) <= 1e-5
