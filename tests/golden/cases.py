@@ -96,3 +96,45 @@ def target_cases():
     labels = torch.tensor([7, 200, 31, 5])
     few = [torch.rand(n, 3, generator=g) - 0.5 + torch.tensor([0., 0., 1.]) for n in (6, 3, 2, 1)]  # < 19 points
     return dict(regular=(lv, boxes, labels), empty_gt=(lv, boxes[:0], labels[:0]), few_points=(few, boxes[:2], labels[:2]))
+
+
+def eval_inputs():
+    """4 scans of ground truth + detections for indoor_eval: jittered copies of the GT (true positives at several IoU
+    levels, duplicates), random false positives, a class that only occurs in the predictions (the nan filter), a class
+    that only occurs in the GT (AP 0) and one paper-thin prediction (the edge clamp). Scores are all distinct."""
+    g = torch.Generator().manual_seed(31)
+    classes = [2, 5, 9, 11, 40]
+    gts, dts = [], []
+    for img in range(4):
+        n = 6 + img
+        ctr = torch.rand(n, 3, generator=g) * torch.tensor([5., 5., 2.]) - torch.tensor([2.5, 2.5, 0.])
+        size = 0.3 + torch.rand(n, 3, generator=g)
+        ang = torch.stack([torch.rand(n, generator=g) * 6.28 - 3.14, 0.1 * torch.randn(n, generator=g),
+                           0.1 * torch.randn(n, generator=g)], 1)
+        boxes = torch.cat([ctr, size, ang], 1)
+        labels = torch.tensor([classes[int(i)] for i in torch.randint(0, len(classes), (n, ), generator=g)])
+        if img == 0:
+            labels[0] = 63                                          # GT-only class
+        pb, ps, pl = [], [], []
+        for i in range(n):
+            for rep in range(int(torch.randint(0, 3, (1, ), generator=g))):   # 0, 1 or 2 detections per GT
+                j = boxes[i].clone()
+                mag = (0.05, 0.25)[rep]
+                j[:3] += mag * size[i] * torch.randn(3, generator=g)
+                j[3:6] *= 1 + mag * torch.randn(3, generator=g).clamp(-1.5, 1.5)
+                j[6:] += 0.3 * mag * torch.randn(3, generator=g)
+                pb.append(j); pl.append(int(labels[i])); ps.append(float(torch.rand(1, generator=g)) * 0.8 + 0.2)
+        for _ in range(5):                                          # false positives, one of a prediction-only class
+            j = torch.cat([torch.rand(3, generator=g) * 4 - 2, 0.3 + torch.rand(3, generator=g),
+                           torch.rand(3, generator=g) - 0.5])
+            pb.append(j); pl.append(int(torch.tensor(classes + [77])[torch.randint(0, 6, (1, ), generator=g)]))
+            ps.append(float(torch.rand(1, generator=g)) * 0.5)
+        thin = boxes[1].clone()
+        thin[3:6] = torch.tensor([0.8, 0.004, 0.01])
+        pb.append(thin); pl.append(int(labels[1])); ps.append(0.15 + 0.01 * img)
+        keep = labels != 63 if img else torch.ones(n, dtype=torch.bool)
+        gts.append(dict(gt_bboxes_3d=boxes.numpy(), gt_labels_3d=labels.numpy()))
+        dts.append(dict(bboxes_3d=torch.stack(pb).numpy(), scores_3d=np.asarray(ps, np.float32),
+                        labels_3d=np.asarray(pl, np.int64)))
+    label2cat = {i: f'class{i}' for i in range(284)}
+    return gts, dts, [0.25, 0.5], label2cat

@@ -28,7 +28,7 @@ import refstubs  # noqa: E402
 
 refstubs.install()
 
-from cases import (det_config, det_inputs, fusion_inputs, occ_config, occ_inputs,  # noqa: E402
+from cases import (det_config, det_inputs, eval_inputs, fusion_inputs, occ_config, occ_inputs,  # noqa: E402
                    preprocess_inputs, target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, fill_tensor  # noqa: E402
 
@@ -294,7 +294,36 @@ def gen_functions():
     save('functions', **out)
 
 
-GENERATORS = dict(detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions)
+def gen_eval():
+    """f3: embodiedscan/eval/indoor_eval.py (indoor_eval -> eval_map_recall -> eval_det_cls -> average_precision)."""
+    import json
+
+    from embodiedscan.eval.indoor_eval import indoor_eval
+    from embodiedscan.structures import EulerDepthInstance3DBoxes
+    import terminaltables
+
+    class _Table:                                   # AsciiTable stand-in: the summary table is only printed
+        def __init__(self, data):
+            self.table = ''
+    terminaltables.AsciiTable = _Table
+    import embodiedscan.eval.indoor_eval as mod
+    mod.AsciiTable = _Table
+    gts, dts, metric, label2cat = eval_inputs()
+    box = lambda a: EulerDepthInstance3DBoxes(torch.from_numpy(a).clone(), box_dim=9, origin=(.5, .5, .5))  # noqa: E731
+    gt_annos = [dict(gt_bboxes_3d=box(gg['gt_bboxes_3d']), gt_labels_3d=gg['gt_labels_3d'].tolist()) for gg in gts]
+    dt_annos = [dict(bboxes_3d=box(d['bboxes_3d']), scores_3d=torch.from_numpy(d['scores_3d']),
+                     labels_3d=torch.from_numpy(d['labels_3d'])) for d in dts]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        from embodiedscan.structures import Box3DMode
+        ret = indoor_eval(gt_annos, dt_annos, metric, label2cat, box_mode_3d=Box3DMode.EULER_DEPTH)
+    print('eval:', {k: round(v, 4) for k, v in ret.items() if k.startswith('m')}, len(ret), 'entries')
+    save('eval', result_json=np.array(json.dumps(ret, sort_keys=True)))
+
+
+GENERATORS = dict(detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions,
+                  eval=gen_eval)
 
 if __name__ == '__main__':
     torch.manual_seed(0)

@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import (det_config, det_inputs, fusion_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
+from cases import (det_config, det_inputs, eval_inputs, fusion_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
                    target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, fill_state_dict  # noqa: E402
 
@@ -227,3 +227,38 @@ def test_product_box_container_matches_reference():
     boxes = target_cases()['regular'][1]
     c = EulerDepthInstance3DBoxes(boxes.clone(), box_dim=9, origin=(.5, .5, .5)).corners
     assert float((c - torch.from_numpy(g['corners'])).abs().max()) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ evaluation (f3)
+def _eval_golden():
+    import json
+    return json.loads(str(load('eval')['result_json']))
+
+
+def test_oracle_indoor_eval_matches_reference():
+    from oracle import eval_ref as E
+    gts, dts, metric, label2cat = eval_inputs()
+    want = _eval_golden()
+    got = E.indoor_eval(gts, dts, metric, label2cat)
+    assert set(got) == set(want)
+    assert 'class77_AP_0.25' not in want and want['class63_AP_0.25'] == 0.0      # nan filter / GT-only class
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-6, (k, got[k], want[k])
+
+
+def test_product_indoor_eval_host_logic_matches_reference():
+    """The product's vectorised AP accumulation with the IoU matrix injected (the CUDA IoU is checked in -m gpu)."""
+    from embodiedscan_b200.evaluation import indoor_eval
+    from oracle import eval_ref as E
+    gts, dts, metric, label2cat = eval_inputs()
+    want = _eval_golden()
+    got = indoor_eval(gts, dts, metric, label2cat,
+                      iou_fn=lambda p, q: torch.from_numpy(E.iou_matrix(p.numpy(), q.numpy())))
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-6, (k, got[k], want[k])
+    with pytest.raises(RuntimeError):
+        if not torch.cuda.is_available():
+            indoor_eval(gts, dts, metric, label2cat)         # no silent CPU fallback for the IoU
+        else:
+            raise RuntimeError('cuda present')

@@ -147,3 +147,23 @@ def test_target_assignment_edge_cases_match_reference(name):
     pos = want_k >= 0
     assert torch.equal(b.cpu()[pos], torch.from_numpy(g[f'targets_{name}_bbox'])[pos])
     assert float((c.cpu()[pos] - torch.from_numpy(g[f'targets_{name}_center'])[pos]).abs().max() if pos.any() else 0.) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ evaluation (f3)
+def test_indoor_eval_matches_reference():
+    """indoor_eval with the 9-DoF IoU from esb_box3d_overlap; every best IoU of the fixture is >= 0.02 away from the
+    thresholds, so the integer part (TP/FP marking) cannot flip under fp32 noise."""
+    import json
+    from embodiedscan_b200.evaluation import IndoorDetMetric, indoor_eval
+    from test_golden_cpu import eval_inputs
+    want = json.loads(str(load('eval')['result_json']))
+    gts, dts, metric, label2cat = eval_inputs()
+    got = indoor_eval(gts, dts, metric, label2cat)
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-5, (k, got[k], want[k])
+    m = IndoorDetMetric(iou_thr=metric)
+    m.dataset_meta = dict(classes=label2cat)
+    m.process(None, [dict(eval_ann_info=g, pred_instances_3d=d) for g, d in zip(gts, dts)])
+    out = m.evaluate()
+    assert abs(out['mAP_0.25'] - want['mAP_0.25']) <= 1e-5
