@@ -138,3 +138,43 @@ def eval_inputs():
                         labels_3d=np.asarray(pl, np.int64)))
     label2cat = {i: f'class{i}' for i in range(284)}
     return gts, dts, [0.25, 0.5], label2cat
+
+
+class HashTextEncoder(torch.nn.Module):
+    """Weight-free stand-in for RoBERTa on BOTH sides of the grounding fixture: hidden states are a fixed smooth function
+    of (token id, position), evaluated in float64 on the CPU and rounded once, so every platform gets the same bits.
+    The text encoder is a library model in the reference and in the product; the fixture pins what consumes its output."""
+
+    def __init__(self, hidden_size=768):
+        super().__init__()
+        self.config = type('Config', (), dict(hidden_size=hidden_size))()
+        self._anchor = torch.nn.Parameter(torch.zeros(1), requires_grad=False)      # gives the module a device
+
+    def forward(self, input_ids, attention_mask=None, **kwargs):
+        ids = input_ids.detach().cpu().double()[..., None]
+        k = torch.arange(self.config.hidden_size, dtype=torch.float64)
+        pos = torch.arange(input_ids.shape[1], dtype=torch.float64)[None, :, None]
+        h = torch.sin(ids * (0.0137 + 0.00011 * k) + 0.5 * k) + 0.3 * torch.cos(pos * 0.21 * (k % 7 + 1))
+        return type('Output', (), dict(last_hidden_state=h.float().to(input_ids.device)))()
+
+
+def ground_config(prune=None):
+    """`prune`: override of MinkNeck's pts_prune_threshold. The training case keeps the small threshold (150) of
+    'C4-small' so that pruning is exercised; the prediction case switches pruning off, because interpolated parent
+    scores tie exactly between sibling voxels and `torch.topk` (the reference) leaves the order of ties unspecified -
+    a tie at the cut would make the fixture depend on the torch build instead of on the reference."""
+    from embodiedscan_b200.synth import mv_grounding_config
+    cfg = mv_grounding_config('C4-small')
+    cfg['backbone_3d']['depth'] = 18
+    if prune is not None:
+        cfg['neck_3d']['pts_prune_threshold'] = prune
+    return cfg
+
+
+def ground_inputs(first_scan=1):
+    from embodiedscan_b200.synth import add_grounding_prompt, synth_batch
+    batch = synth_batch(first_scan, 2, n_views=2, H=240, W=320, n_points=2000)
+    batch['inputs']['points'] = [division_safe(p) for p in batch['inputs']['points']]
+    for i, ds in enumerate(batch['data_samples']):
+        add_grounding_prompt(ds, 1 + 2 * i, seed=i)
+    return batch

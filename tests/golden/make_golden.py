@@ -28,9 +28,9 @@ import refstubs  # noqa: E402
 
 refstubs.install()
 
-from cases import (det_config, det_inputs, eval_inputs, fusion_inputs, occ_config, occ_inputs,  # noqa: E402
+from cases import (HashTextEncoder, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs,  # noqa: E402
                    preprocess_inputs, target_cases, unproject_inputs)
-from weights import adjust_fcaf3d_head, adjust_for_predict, fill_tensor  # noqa: E402
+from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_tensor  # noqa: E402
 
 
 def _np(x):
@@ -95,6 +95,8 @@ def ref_data_samples(data_samples):
         r.gt_instances_3d = gt
         if hasattr(ds, 'gt_occupancy'):
             r.gt_occupancy = ds.gt_occupancy.clone()
+        if hasattr(ds, 'text'):
+            r.text, r.tokens_positive = ds.text, ds.tokens_positive
         out.append(r)
     return out
 
@@ -322,7 +324,79 @@ def gen_eval():
     save('eval', result_json=np.array(json.dumps(ret, sort_keys=True)))
 
 
-GENERATORS = dict(detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions,
+GROUND_WATCH = ('bbox_head.reg_branches.0.4.weight', 'bbox_head.cls_branches.0.bias', 'text_feat_map.weight',
+                'decoder.layers.0.cross_attn.attn.in_proj_weight', 'decoder.layers.1.ffn.layers.1.weight',
+                'decoder.cross_posembed.position_embedding_head.0.weight', 'neck_3d.out_block_0.0.kernel',
+                'neck_3d.up_block_2.0.kernel', 'backbone_3d.conv1.kernel', 'backbone.layer2.0.conv1.weight')
+
+
+def _config_dict(x):
+    from mmengine import ConfigDict
+    if isinstance(x, dict):
+        return ConfigDict({k: _config_dict(v) for k, v in x.items()})
+    if isinstance(x, list):
+        return [_config_dict(v) for v in x]
+    return x
+
+
+def gen_grounding():
+    """a15: SparseFeatureFusion3DGrounder (sparse_featfusion_grounder.py) -> MinkNeck -> pre_decoder (top-k queries) ->
+    SparseFeatureFusionTransformerDecoder -> GroundingHead.loss (HungarianAssigner3D + match costs + focal + BBoxCDLoss)
+    and .predict.  RoBERTa + its tokenizer are replaced on both sides by HashTextEncoder + the product's
+    SimpleTokenizer (the pretrained files need a network); `get_positive_map` is the reference's own and is pinned."""
+    import copy
+
+    import embodiedscan.models  # noqa: F401
+    import embodiedscan.models.detectors.sparse_featfusion_grounder as GM
+    from embodiedscan.registry import MODELS
+    from embodiedscan_b200.grounding import SimpleTokenizer
+    from oracle import model_ref as M
+    GM.RobertaTokenizerFast = type('Tok', (), dict(from_pretrained=staticmethod(lambda t: SimpleTokenizer())))
+    GM.RobertaModel = type('Enc', (), dict(from_pretrained=staticmethod(lambda t: HashTextEncoder())))
+    cfg = ground_config()
+    c = copy.deepcopy(cfg)
+    c.pop('data_preprocessor')
+    model = MODELS.build(_config_dict(c))
+    manifest = fill_module(model, adjust_grounder)
+    out = manifest_arrays(manifest)
+
+    def inputs(first_scan):
+        batch = ground_inputs(first_scan)
+        imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                                 cfg['data_preprocessor']['std'])
+        return dict(points=batch['inputs']['points'], imgs=imgs), ref_data_samples(batch['data_samples'])
+    x, ds = inputs(1)
+    calib = calibrate_norms(model, lambda: model(x, ds, mode='loss'))
+    out.update(calib)
+    model.train()
+    x, ds = inputs(1)
+    losses = model(x, ds, mode='loss')
+    sum(losses.values()).backward()
+    for k, v in losses.items():
+        out['a_' + k] = v
+    for i, d in enumerate(ds):
+        out[f'a_positive_map_{i}'] = d.gt_instances_3d.positive_maps
+    params = dict(model.named_parameters())
+    for k in GROUND_WATCH:
+        g = params[k].grad
+        out[f'a_grad/{k}'] = g if g.numel() <= 4096 else g.flatten()[:: max(g.numel() // 4096, 1)][:4096]
+        out[f'a_gradnorm/{k}'] = g.double().norm()
+    sd = adjust_grounder({k: fill_tensor(k, sh) for k, sh in manifest})
+    sd.update({k[len('calib/'):]: v for k, v in calib.items()})
+    model.load_state_dict(sd)
+    model.eval()
+    model.neck_3d.pts_prune_threshold = ground_config(prune=100000)['neck_3d']['pts_prune_threshold']
+    x, ds = inputs(3)
+    with torch.no_grad():
+        res = model(x, ds, mode='predict')
+    for i, r in enumerate(res):
+        out[f'p_scores_{i}'] = r.pred_instances_3d.scores_3d
+        out[f'p_boxes_{i}'] = r.pred_instances_3d.bboxes_3d.tensor
+    print('grounding: losses', {k: round(float(v.detach()), 5) for k, v in losses.items()})
+    save('grounding_g4', **out)
+
+
+GENERATORS = dict(grounding=gen_grounding, detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions,
                   eval=gen_eval)
 
 if __name__ == '__main__':

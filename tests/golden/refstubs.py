@@ -256,6 +256,56 @@ class BaseTransform:
         return self.transform(results)
 
 
+class MultiheadAttention(nn.Module):
+    """mmcv.cnn.bricks.transformer.MultiheadAttention (2.0.0rc4, restated from its published source): positional
+    encodings added to query/key, `nn.MultiheadAttention` in (L, B, E) layout, residual `identity + proj(attn)`."""
+
+    def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0., dropout_layer=None, init_cfg=None,
+                 batch_first=False, dropout=None, **kwargs):
+        super().__init__()
+        assert not attn_drop and not proj_drop and not dropout
+        self.embed_dims, self.num_heads, self.batch_first = embed_dims, num_heads, batch_first
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, 0.0, **kwargs)
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, attn_mask=None,
+                key_padding_mask=None, **kwargs):
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        if identity is None:
+            identity = query
+        if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
+            key_pos = query_pos
+        if query_pos is not None:
+            query = query + query_pos
+        if key_pos is not None:
+            key = key + key_pos
+        if self.batch_first:
+            query, key, value = query.transpose(0, 1), key.transpose(0, 1), value.transpose(0, 1)
+        out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask, key_padding_mask=key_padding_mask)[0]
+        if self.batch_first:
+            out = out.transpose(0, 1)
+        return identity + out
+
+
+class FFN(nn.Module):
+    """mmcv.cnn.bricks.transformer.FFN: Sequential(Sequential(Linear, act, Dropout) x (num_fcs-1), Linear, Dropout),
+    residual added."""
+
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2, act_cfg=dict(type='ReLU', inplace=True),
+                 ffn_drop=0., dropout_layer=None, add_identity=True, init_cfg=None, **kwargs):
+        super().__init__()
+        assert num_fcs == 2 and not ffn_drop and add_identity
+        self.embed_dims = embed_dims
+        self.layers = nn.Sequential(nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True),
+                                                  nn.Dropout(0.)),
+                                    nn.Linear(feedforward_channels, embed_dims), nn.Dropout(0.))
+
+    def forward(self, x, identity=None):
+        return (x if identity is None else identity) + self.layers(x)
+
+
 def _nms3d(boxes, scores, iou_threshold):
     from oracle import geometry_ref as G
     keep = G.nms3d(boxes.detach().cpu().numpy().astype(np.float32), scores.detach().cpu().numpy(), iou_threshold)
@@ -285,7 +335,8 @@ def _install_mmcv():
         return t.lower() + str(postfix), layer(num_features, **cfg)
     cnn.build_norm_layer = build_norm_layer
     _mod('mmcv.cnn.bricks')
-    _mod('mmcv.cnn.bricks.transformer')
+    tr = _mod('mmcv.cnn.bricks.transformer')
+    tr.MultiheadAttention, tr.FFN = MultiheadAttention, FFN
     _mod('mmcv.utils').ext_loader = _Dummy()
 
 
@@ -451,9 +502,10 @@ class FocalLoss(nn.Module):
     def __init__(self, use_sigmoid=True, gamma=2.0, alpha=0.25, reduction='mean', loss_weight=1.0, activated=False):
         super().__init__()
         self.gamma, self.alpha, self.reduction, self.loss_weight = gamma, alpha, reduction, loss_weight
+        self.use_sigmoid, self.activated = use_sigmoid, activated
 
     def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
-        if target.dim() == 1:
+        if pred.dim() != target.dim():                 # integer labels; same rank = already a (soft) one-hot target
             target = (target[:, None] == torch.arange(pred.shape[1])[None]).to(pred.dtype)
         else:
             target = target.to(pred.dtype)

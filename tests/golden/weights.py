@@ -51,3 +51,15 @@ def adjust_for_predict(sd: dict, prefix: str = 'bbox_head.') -> dict:
     sd[prefix + 'conv_cls.kernel'] = sd[prefix + 'conv_cls.kernel'] * 5.0
     sd[prefix + 'conv_center.kernel'] = sd[prefix + 'conv_center.kernel'] * 20.0
     return sd
+
+
+def adjust_grounder(sd: dict) -> dict:
+    """`share_pred_layer=True`: every `bbox_head.{cls,reg}_branches.i` IS entry 0 (grounding_head.py:205-214), so the
+    name-keyed fill must give the aliases one value. In place; returns `sd`."""
+    for k in list(sd):
+        for kind in ('cls_branches', 'reg_branches'):
+            tag = f'bbox_head.{kind}.'
+            if k.startswith(tag) and not k.startswith(tag + '0.'):
+                i, rest = k[len(tag):].split('.', 1)
+                sd[k] = sd[tag + '0.' + rest]
+    return sd

@@ -15,9 +15,9 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import (det_config, det_inputs, eval_inputs, fusion_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
+from cases import (HashTextEncoder, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
                    target_cases, unproject_inputs)
-from weights import adjust_fcaf3d_head, adjust_for_predict, fill_state_dict  # noqa: E402
+from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_state_dict  # noqa: E402
 
 
 def load(name):
@@ -262,3 +262,96 @@ def test_product_indoor_eval_host_logic_matches_reference():
             indoor_eval(gts, dts, metric, label2cat)         # no silent CPU fallback for the IoU
         else:
             raise RuntimeError('cuda present')
+
+
+# ------------------------------------------------------------------------------------------------ grounding (a15)
+GROUND_WATCH = {'bbox_head.reg_branches.0.4.weight': None, 'bbox_head.cls_branches.0.bias': None,
+                'text_feat_map.weight': None, 'decoder.layers.0.cross_attn.attn.in_proj_weight': None,
+                'decoder.layers.1.ffn.layers.1.weight': None,
+                'decoder.cross_posembed.position_embedding_head.0.weight': None, 'neck_3d.out_block_0.0.kernel': None,
+                'neck_3d.up_block_2.0.kernel': None, 'backbone_3d.conv1.kernel': None,
+                'backbone.layer2.0.conv1.weight': 'backbone.layer2.0.cb1.conv.weight'}
+
+
+def build_grounder(g, prune=None):
+    """Product grounder with the fixture's weights and the weight-free text encoder of the fixture."""
+    import warnings
+    from embodiedscan_b200 import MODELS
+    cfg = ground_config(prune)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        model = MODELS.build(cfg)
+    model.text_encoder = HashTextEncoder()
+    ref_sd = adjust_grounder(fill_state_dict(manifest(g)))
+    ref_sd.update({k[len('calib/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('calib/')})
+    missing, unexpected = model.load_state_dict(ref_sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith('num_batches_tracked') for k in missing), missing
+    return cfg, model
+
+
+def grounder_text_side(model, batch):
+    """Tokenisation, positive maps (host logic of the product) and the text encoder's hidden states."""
+    tok = model.tokenizer.batch_encode_plus([d.text for d in batch['data_samples']], padding='longest')
+    pos_maps = [m.bool().float() for m in model.get_positive_map(tok, [d.tokens_positive for d in batch['data_samples']])]
+    hidden = model.text_encoder(**tok).last_hidden_state.float().cpu()
+    return hidden, tok.attention_mask.bool(), pos_maps
+
+
+def alias_shared_branches(sd):
+    for k in list(sd):
+        for kind in ('cls_branches', 'reg_branches'):
+            tag = f'bbox_head.{kind}.'
+            if k.startswith(tag) and not k.startswith(tag + '0.'):
+                sd[k] = sd[tag + '0.' + k[len(tag):].split('.', 1)[1]]
+    return sd
+
+
+def test_grounder_loss_and_gradients_match_reference():
+    from oracle import ground_ref as R
+    from oracle import model_ref as M
+    g = load('grounding_g4')
+    cfg, model = build_grounder(g)
+    batch = ground_inputs(1)
+    hidden, tmask, pos_maps = grounder_text_side(model, batch)
+    for i, pm in enumerate(pos_maps):
+        assert torch.equal(pm, torch.from_numpy(g[f'a_positive_map_{i}'])), 'token spans of the targets'
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for ref_name, own in GROUND_WATCH.items():
+        k = own or ref_name
+        sd[k] = sd[k].clone().requires_grad_(True)
+    sd = alias_shared_branches(sd)
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    out, _ = R.grounder_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'], hidden, tmask, pos_maps)
+    sum(out.values()).backward()
+    assert {'a_' + k for k in out} == {k for k in g.files if k.startswith('a_') and 'loss' in k}
+    for k in out:
+        assert rel(out[k], g['a_' + k]) <= 5e-5, (k, float(out[k]), float(g['a_' + k]))
+    for ref_name, own in GROUND_WATCH.items():
+        grad = sd[own or ref_name].grad
+        want = torch.from_numpy(g[f'a_grad/{ref_name}'])
+        got = sampled(grad).reshape(want.shape)
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 5e-4 * scale, (ref_name, float((got - want).abs().max()), scale)
+        assert rel(grad.double().norm(), g[f'a_gradnorm/{ref_name}']) <= 5e-4, ref_name
+
+
+def test_grounder_predictions_match_reference():
+    from oracle import ground_ref as R
+    from oracle import model_ref as M
+    g = load('grounding_g4')
+    cfg, model = build_grounder(g, prune=100000)
+    batch = ground_inputs(3)
+    hidden, tmask, _ = grounder_text_side(model, batch)
+    sd = alias_shared_branches({k: v.detach().clone() for k, v in model.state_dict().items()})
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    with torch.no_grad():
+        cls, boxes = R.grounder_forward(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'], hidden, tmask,
+                                        False)
+    for b in range(2):
+        scores = cls[-1][b].sigmoid().max(-1)[0]
+        assert float((scores - torch.from_numpy(g[f'p_scores_{b}'])).abs().max()) <= 5e-5
+        want = torch.from_numpy(g[f'p_boxes_{b}'])
+        assert float((boxes[-1][b] - want).abs().max()) <= 1e-4 * float(want.abs().max())

@@ -6,7 +6,7 @@ Bar (BASELINE.json north_star): selection order / labels identical, fp32 values 
 import pytest
 import torch
 
-from test_golden_cpu import (MEAN, fusion_inputs, target_cases, OCC_WATCH, STD, WATCH, preprocess_inputs, unproject_inputs, check_occupancy_prediction, occ_config, occ_inputs, adjust_fcaf3d_head, adjust_for_predict, det_config, det_inputs, load,
+from test_golden_cpu import (GROUND_WATCH, MEAN, build_grounder, ground_inputs, fusion_inputs, target_cases, OCC_WATCH, STD, WATCH, preprocess_inputs, unproject_inputs, check_occupancy_prediction, occ_config, occ_inputs, adjust_fcaf3d_head, adjust_for_predict, det_config, det_inputs, load,
                              product_state_dict, rel, sampled)
 
 pytestmark = pytest.mark.gpu
@@ -167,3 +167,45 @@ def test_indoor_eval_matches_reference():
     m.process(None, [dict(eval_ann_info=g, pred_instances_3d=d) for g, d in zip(gts, dts)])
     out = m.evaluate()
     assert abs(out['mAP_0.25'] - want['mAP_0.25']) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ grounding (a15)
+def test_grounder_loss_and_gradients_match_reference():
+    g = load('grounding_g4')
+    cfg, model = build_grounder(g)
+    model = model.to(DEV).train()
+    batch = ground_inputs(1)
+    data = model.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # fp32 parity arithmetic; the backward pass reads the global flag
+    try:
+        losses = model(**data, mode='loss')
+        sum(losses.values()).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    for i, ds in enumerate(batch['data_samples']):
+        assert torch.equal(ds.gt_instances_3d.positive_maps.cpu(), torch.from_numpy(g[f'a_positive_map_{i}']))
+    assert {'a_' + k for k in losses} == {k for k in g.files if k.startswith('a_') and 'loss' in k}
+    for k in losses:
+        assert rel(losses[k], g['a_' + k]) <= 1e-3, (k, float(losses[k]), float(g['a_' + k]))
+    params = dict(model.named_parameters())
+    for ref_name, own in GROUND_WATCH.items():
+        grad = params[own or ref_name].grad.detach().cpu()
+        want = torch.from_numpy(g[f'a_grad/{ref_name}'])
+        got = sampled(grad).reshape(want.shape)
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 5e-3 * scale, (ref_name, float((got - want).abs().max()), scale)
+        assert rel(grad.double().norm(), g[f'a_gradnorm/{ref_name}']) <= 5e-3, ref_name
+
+
+def test_grounder_predictions_match_reference():
+    g = load('grounding_g4')
+    cfg, model = build_grounder(g, prune=100000)
+    model = model.to(DEV).eval()
+    batch = ground_inputs(3)
+    with torch.no_grad():
+        out = model.val_step(dict(inputs=batch['inputs'], data_samples=batch['data_samples']))
+    for b, ds in enumerate(out):
+        want_s, want_b = torch.from_numpy(g[f'p_scores_{b}']), torch.from_numpy(g[f'p_boxes_{b}'])
+        assert float((ds.pred_instances_3d.scores_3d.cpu() - want_s).abs().max()) <= 1e-3
+        assert float((ds.pred_instances_3d.bboxes_3d.tensor.cpu() - want_b).abs().max()) <= 1e-3 * float(want_b.abs().max())
