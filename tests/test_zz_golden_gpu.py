@@ -2,7 +2,10 @@
 Python (tests/golden/make_golden.py; fixtures committed under tests/golden/).  Nothing here touches the oracle or
 /root/reference: weights come from the stored manifest + name-keyed fill, inputs from the seeded generators.
 
-Bar (BASELINE.json north_star): selection order / labels identical, fp32 values within 1e-3 relative."""
+Bar (BASELINE.json north_star): selection order / labels identical, fp32 values within 1e-3 relative.
+
+The file name sorts last on purpose: these tests were written after round 1's GPU budget was spent, so they run after
+the oracle-parity files that were green on the B200 (`-x` stops at the first failure)."""
 import pytest
 import torch
 
