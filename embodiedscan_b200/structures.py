@@ -122,6 +122,63 @@ class EulerDepthInstance3DBoxes:
         out = EulerDepthInstance3DBoxes(self.tensor.to(device), box_dim=9, with_yaw=self.with_yaw)
         return out
 
+    # ---- augmentation (euler_box3d.py:186-281, euler_depth_box3d.py:49-78, base_box3d.py:248-257); torch ops on
+    # whatever device the box tensor lives on ----
+    def transform(self, matrix):
+        """Apply a 4x4 rigid transform: centres move, Euler angles become ZXY(matrix_R @ R(angles))."""
+        from .geometry import euler_angles_to_matrix, matrix_to_euler_angles_zxy
+        if self.tensor.shape[0] == 0:
+            return
+        matrix = torch.as_tensor(matrix, dtype=self.tensor.dtype, device=self.tensor.device)
+        pts = torch.cat([self.tensor[:, :3], self.tensor.new_ones(self.tensor.shape[0], 1)], -1)
+        ctr = torch.matmul(pts, matrix.transpose(-2, -1))[:, :3]
+        ori = euler_angles_to_matrix(self.tensor[:, 6:], 'ZXY')
+        ang = matrix_to_euler_angles_zxy(torch.bmm(matrix[:3, :3].expand_as(ori), ori))
+        self.tensor = torch.cat([ctr, self.tensor[:, 3:6], ang], -1)
+
+    def rotate(self, angle, points=None):
+        """`angle`: yaw (scalar), 3 ZXY Euler angles or a 3x3 matrix. Rotates the boxes and, when given, `points`
+        ((N, >=3) tensor, in place); returns (points, rot_mat_T) or rot_mat_T like the reference."""
+        from .geometry import euler_angles_to_matrix
+        angle = torch.as_tensor(angle, dtype=self.tensor.dtype, device=self.tensor.device)
+        if angle.numel() == 1:
+            rot = euler_angles_to_matrix(torch.stack([angle.reshape(()), angle.new_zeros(()), angle.new_zeros(())]), 'ZXY')
+        elif angle.numel() == 3:
+            rot = euler_angles_to_matrix(angle.reshape(3), 'ZXY')
+        else:
+            assert angle.shape == (3, 3)
+            rot = angle
+        m = torch.eye(4, dtype=self.tensor.dtype, device=self.tensor.device)
+        m[:3, :3] = rot
+        self.transform(m)
+        rot_mat_T = rot.T
+        if points is not None:
+            points[:, :3] = points[:, :3] @ rot_mat_T.to(points.device)
+            return points, rot_mat_T
+        return rot_mat_T
+
+    def flip(self, bev_direction='horizontal', points=None):
+        """Depth coordinates: 'horizontal' mirrors x, 'vertical' mirrors y (boxes, and `points` in place when given)."""
+        import math
+        assert bev_direction in ('horizontal', 'vertical')
+        if bev_direction == 'horizontal':
+            self.tensor[:, 0] = -self.tensor[:, 0]
+            self.tensor[:, 6] = -self.tensor[:, 6] + math.pi
+            self.tensor[:, 8] = -self.tensor[:, 8]
+        else:
+            self.tensor[:, 1] = -self.tensor[:, 1]
+            self.tensor[:, 6] = -self.tensor[:, 6]
+            self.tensor[:, 7] = -self.tensor[:, 7] + math.pi
+        if points is not None:
+            points[:, 0 if bev_direction == 'horizontal' else 1] *= -1
+            return points
+
+    def scale(self, scale_factor: float):
+        self.tensor[:, :6] *= scale_factor
+
+    def translate(self, trans_vector):
+        self.tensor[:, :3] += torch.as_tensor(trans_vector, dtype=self.tensor.dtype, device=self.tensor.device)
+
     @classmethod
     def overlaps(cls, boxes1, boxes2, mode='iou', eps=1e-4):
         """(N,M) 9-DoF 3D IoU (euler_box3d.py:103-135)."""

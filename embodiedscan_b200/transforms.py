@@ -2,6 +2,13 @@
 launch, replacing LoadDepthFromFile's `/ depth_shift`, ConvertRGBDToPoints + points_img2cam and AggregateMultiViewPoints
 (embodiedscan/datasets/transforms/loading.py:70-73, points.py:30-81, structures/bbox_3d/utils.py:335-368,
 multiview.py:139-169), followed by the reference's two PointSample stages (points.py:119-153) as seeded permutations.
+
+The 3D augmentations of the training pipeline (configs/detection/mv-det3d_*.py:147-158) follow as torch operations on
+the device-resident points and the (tiny) box tensor: `RandomFlip3D` (datasets/transforms/augmentation.py:11-250, the
+`flip_2d=False` configuration) and `GlobalRotScaleTrans` (:253-420). They draw from `numpy.random` in the reference's
+order, so a seeded run makes the same decisions as the reference pipeline, and they record the same `img_meta` keys
+(`pcd_horizontal_flip`, `pcd_vertical_flip`, `pcd_rotation`, `pcd_scale_factor`, `pcd_trans`,
+`transformation_3d_flow`) that point painting reverses (fusion.py).
 """
 from typing import Optional, Sequence
 
@@ -66,3 +73,101 @@ class MultiViewDepthToPoints:
         keep = keep[torch.randperm(keep.numel(), generator=gen, device=pts.device)[:self.num_points]]
         results['points'] = pts[keep].contiguous()
         return results
+
+
+@TRANSFORMS.register_module()
+class RandomFlip3D:
+    """BEV flips of points + 9-DoF boxes. Only the configured mode is implemented: 3D flips decided independently of the
+    images (``sync_2d=False, flip_2d=False``)."""
+
+    def __init__(self, sync_2d: bool = True, flip_2d: bool = True, flip_3d: bool = True,
+                 flip_ratio_bev_horizontal: float = 0.0, flip_ratio_bev_vertical: float = 0.0, flip_box3d: bool = True,
+                 **kwargs):
+        assert not flip_2d and not sync_2d, 'image flips are not on the configured path (cfg :147-152)'
+        self.flip_3d, self.flip_box3d = flip_3d, flip_box3d
+        self.flip_ratio_bev_horizontal, self.flip_ratio_bev_vertical = flip_ratio_bev_horizontal, flip_ratio_bev_vertical
+
+    def _flip(self, results, direction):
+        if 'gt_bboxes_3d' in results and self.flip_box3d:
+            if 'points' in results:
+                results['points'] = results['gt_bboxes_3d'].flip(direction, points=results['points'])
+            else:
+                results['gt_bboxes_3d'].flip(direction)
+        elif 'points' in results:
+            results['points'][:, 0 if direction == 'horizontal' else 1] *= -1
+
+    def __call__(self, results: dict) -> dict:
+        if not self.flip_3d:
+            return results
+        if 'pcd_horizontal_flip' not in results:
+            results['pcd_horizontal_flip'] = bool(np.random.rand() < self.flip_ratio_bev_horizontal)
+        if 'pcd_vertical_flip' not in results:
+            results['pcd_vertical_flip'] = bool(np.random.rand() < self.flip_ratio_bev_vertical)
+        flow = results.setdefault('transformation_3d_flow', [])
+        if results['pcd_horizontal_flip']:
+            self._flip(results, 'horizontal')
+            flow.extend(['HF'])
+        if results['pcd_vertical_flip']:
+            self._flip(results, 'vertical')
+            flow.extend(['VF'])
+        return results
+
+    transform = __call__
+
+
+@TRANSFORMS.register_module()
+class GlobalRotScaleTrans:
+    """Random yaw (or 3-DoF) rotation, isotropic scale and Gaussian translation of points + boxes."""
+
+    def __init__(self, rot_range=(-0.78539816, 0.78539816), rot_dof: int = 1, scale_ratio_range=(0.95, 1.05),
+                 translation_std=(0, 0, 0), shift_height: bool = False, **kwargs):
+        if not isinstance(rot_range, (list, tuple, np.ndarray)):
+            rot_range = [-rot_range, rot_range]
+        if not isinstance(translation_std, (list, tuple, np.ndarray)):
+            translation_std = [translation_std] * 3
+        assert not shift_height
+        self.rot_range, self.rot_dof = rot_range, rot_dof
+        self.scale_ratio_range, self.translation_std = scale_ratio_range, translation_std
+
+    def __call__(self, results: dict) -> dict:
+        flow = results.setdefault('transformation_3d_flow', [])
+        pts, boxes = results.get('points'), results.get('gt_bboxes_3d')
+        # rotation (augmentation.py:330-362)
+        if self.rot_dof == 1:
+            noise = -np.random.uniform(self.rot_range[0], self.rot_range[1])
+        else:
+            noise = np.array([-np.random.uniform(self.rot_range[0], self.rot_range[1]) for _ in range(3)])
+        if boxes is not None and len(boxes.tensor) != 0:
+            if pts is not None:
+                pts, rot_mat_T = boxes.rotate(noise, pts)
+                results['points'] = pts
+            else:
+                rot_mat_T = boxes.rotate(noise)
+        elif pts is not None:
+            from .geometry import euler_angles_to_matrix
+            ang = torch.as_tensor(noise, dtype=pts.dtype, device=pts.device).reshape(-1)
+            if ang.numel() == 1:
+                ang = torch.cat([ang, ang.new_zeros(2)])
+            rot_mat_T = euler_angles_to_matrix(ang, 'ZXY').T
+            pts[:, :3] = pts[:, :3] @ rot_mat_T
+        results['pcd_rotation'] = rot_mat_T
+        results['pcd_rotation_angle'] = noise
+        # scale (:364-395)
+        if 'pcd_scale_factor' not in results:
+            results['pcd_scale_factor'] = np.random.uniform(self.scale_ratio_range[0], self.scale_ratio_range[1])
+        scale = results['pcd_scale_factor']
+        if pts is not None:
+            pts[:, :3] *= scale
+        if boxes is not None:
+            boxes.scale(scale)
+        # translation (:309-328)
+        trans = np.random.normal(scale=np.array(self.translation_std, dtype=np.float32), size=3).T
+        if pts is not None:
+            pts[:, :3] += torch.as_tensor(trans, dtype=pts.dtype, device=pts.device)
+        results['pcd_trans'] = trans
+        if boxes is not None:
+            boxes.translate(trans)
+        flow.extend(['R', 'S', 'T'])
+        return results
+
+    transform = __call__

@@ -178,3 +178,11 @@ def ground_inputs(first_scan=1):
     for i, ds in enumerate(batch['data_samples']):
         add_grounding_prompt(ds, 1 + 2 * i, seed=i)
     return batch
+
+
+def augment_inputs():
+    """Points + GT boxes of scan 5 for the 3D augmentations; `seed` makes numpy draw both flips."""
+    from embodiedscan_b200.synth import synth_scan
+    s = synth_scan(5, n_views=2, H=48, W=64, n_points=500)
+    boxes = s['data_sample'].gt_instances_3d.bboxes_3d.tensor.clone()
+    return s['points'].clone(), boxes, 2

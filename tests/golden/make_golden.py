@@ -28,7 +28,7 @@ import refstubs  # noqa: E402
 
 refstubs.install()
 
-from cases import (HashTextEncoder, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs,  # noqa: E402
+from cases import (HashTextEncoder, augment_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs,  # noqa: E402
                    preprocess_inputs, target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_tensor  # noqa: E402
 
@@ -396,7 +396,28 @@ def gen_grounding():
     save('grounding_g4', **out)
 
 
-GENERATORS = dict(grounding=gen_grounding, detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions,
+def gen_augment():
+    """f1: RandomFlip3D (augmentation.py:11-250, flip_2d=False) then GlobalRotScaleTrans (:253-447) with the config's
+    parameters, on the reference's DepthPoints + EulerDepthInstance3DBoxes; numpy's global RNG is seeded."""
+    from embodiedscan.datasets.transforms.augmentation import GlobalRotScaleTrans, RandomFlip3D
+    from embodiedscan.structures import EulerDepthInstance3DBoxes
+    from embodiedscan.structures.points import DepthPoints
+    pts, boxes, seed = augment_inputs()
+    np.random.seed(seed)
+    d = dict(points=DepthPoints(pts.clone(), points_dim=3),
+             gt_bboxes_3d=EulerDepthInstance3DBoxes(boxes.clone(), box_dim=9, origin=(.5, .5, .5)))
+    d = RandomFlip3D(sync_2d=False, flip_2d=False, flip_ratio_bev_horizontal=0.5, flip_ratio_bev_vertical=0.5) \
+        .transform(d)
+    d = GlobalRotScaleTrans(rot_range=[-0.087266, 0.087266], scale_ratio_range=[.9, 1.1],
+                            translation_std=[.1, .1, .1], shift_height=False).transform(d)
+    print('augment: flow', d['transformation_3d_flow'], 'HF', d['pcd_horizontal_flip'], 'VF', d['pcd_vertical_flip'])
+    assert d['pcd_horizontal_flip'] and d['pcd_vertical_flip'], 'pick a seed that draws both flips'
+    save('augment', points=d['points'].tensor, boxes=d['gt_bboxes_3d'].tensor, pcd_rotation=d['pcd_rotation'],
+         pcd_scale_factor=np.float64(d['pcd_scale_factor']), pcd_trans=d['pcd_trans'],
+         flow=np.array(d['transformation_3d_flow']))
+
+
+GENERATORS = dict(augment=gen_augment, grounding=gen_grounding, detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions,
                   eval=gen_eval)
 
 if __name__ == '__main__':

@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import (HashTextEncoder, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
+from cases import (HashTextEncoder, augment_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
                    target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_state_dict  # noqa: E402
 
@@ -355,3 +355,35 @@ def test_grounder_predictions_match_reference():
         assert float((scores - torch.from_numpy(g[f'p_scores_{b}'])).abs().max()) <= 5e-5
         want = torch.from_numpy(g[f'p_boxes_{b}'])
         assert float((boxes[-1][b] - want).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ augmentation (f1)
+def test_device_augmentations_match_reference():
+    """RandomFlip3D + GlobalRotScaleTrans of the product are torch ops on whatever device holds the points: the same
+    code runs here on CPU tensors. Same numpy seed -> same draws as the reference pipeline."""
+    from embodiedscan_b200.structures import EulerDepthInstance3DBoxes
+    from embodiedscan_b200.transforms import GlobalRotScaleTrans, RandomFlip3D
+    g = load('augment')
+    pts, boxes, seed = augment_inputs()
+    np.random.seed(seed)
+    d = dict(points=pts.clone(), gt_bboxes_3d=EulerDepthInstance3DBoxes(boxes.clone(), box_dim=9))
+    d = RandomFlip3D(sync_2d=False, flip_2d=False, flip_ratio_bev_horizontal=0.5, flip_ratio_bev_vertical=0.5)(d)
+    d = GlobalRotScaleTrans(rot_range=[-0.087266, 0.087266], scale_ratio_range=[.9, 1.1], translation_std=[.1, .1, .1],
+                            shift_height=False)(d)
+    assert d['transformation_3d_flow'] == g['flow'].tolist() == ['HF', 'VF', 'R', 'S', 'T']
+    assert float(d['pcd_scale_factor']) == float(g['pcd_scale_factor'])
+    assert np.array_equal(np.asarray(d['pcd_trans']), g['pcd_trans'])
+    assert float((torch.as_tensor(d['pcd_rotation']) - torch.from_numpy(g['pcd_rotation'])).abs().max()) <= 1e-7
+    assert float((d['points'] - torch.from_numpy(g['points'])).abs().max()) <= 1e-6
+    got, want = d['gt_bboxes_3d'].tensor, torch.from_numpy(g['boxes'])
+    assert float((got[:, :6] - want[:, :6]).abs().max()) <= 1e-6
+    # Euler angles modulo 2*pi (both sides go through matrix -> ZXY angles)
+    dang = torch.remainder(got[:, 6:] - want[:, 6:] + np.pi, 2 * np.pi) - np.pi
+    assert float(dang.abs().max()) <= 1e-5
+    # and the painting side reverses exactly this flow: augmented points map back onto the original ones
+    from oracle import model_ref as M
+    meta = {k: d[k] for k in ('transformation_3d_flow', 'pcd_horizontal_flip', 'pcd_vertical_flip', 'pcd_scale_factor',
+                              'pcd_trans')}
+    meta['pcd_rotation'] = torch.as_tensor(d['pcd_rotation']).numpy()
+    back = M.apply_3d_transformation_reverse(d['points'], meta)
+    assert float((back - pts).abs().max()) <= 1e-5
