@@ -16,7 +16,7 @@ from . import sparse as SP
 from ._ffi import call, ptr, stream
 from .fusion import pack_paint_metas, pack_projections, paint_points
 from .registry import MODELS
-from .structures import InstanceData
+from .structures import Det3DDataSample, InstanceData
 
 
 @MODELS.register_module()
@@ -25,7 +25,7 @@ class Det3DDataPreprocessor(nn.Module):
     of ``pad_size_divisor``, multi-view stack; points pass through (``voxel=False`` is the only configured mode)."""
 
     def __init__(self, mean=None, std=None, bgr_to_rgb=False, rgb_to_bgr=False, pad_size_divisor=1, pad_value=0,
-                 voxel=False, non_blocking=False, compute_dtype=torch.float32, **kwargs):
+                 voxel=False, non_blocking=False, compute_dtype=torch.float32, batchwise_inputs=False, **kwargs):
         super().__init__()
         assert not voxel, 'mmcv voxelisation wrappers are not on any configured path (SURVEY N14)'
         assert not (bgr_to_rgb and rgb_to_bgr)
@@ -34,18 +34,52 @@ class Det3DDataPreprocessor(nn.Module):
         self.std = [float(s) for s in (std or [1., 1., 1.])]
         self.pad_size_divisor, self.pad_value = pad_size_divisor, pad_value
         self.compute_dtype = compute_dtype
+        self.batchwise_inputs = batchwise_inputs
         self.register_buffer('_dev', torch.zeros(1), persistent=False)
 
     @property
     def device(self):
         return self._dev.device
 
+    @staticmethod
+    def split_batchwise(data_samples):
+        """`batchwise_inputs=True` (data_preprocessor.py:172-205): ONE scan whose annotations are lists over its 1..N
+        frame prefixes becomes N data samples sharing the scan's metainfo (continuous 3D perception)."""
+        first = data_samples[0]
+        gt = first.gt_instances_3d
+        labels = gt.labels_3d
+        assert isinstance(labels, list), 'continuous inputs carry per-prefix lists (ConstructMultiSweeps)'
+        boxes = gt.bboxes_3d if 'bboxes_3d' in gt else None
+        masks = list(first.gt_occupancy_masks) if 'gt_occupancy_masks' in first else None
+        ann = first.eval_ann_info if 'eval_ann_info' in first and first.eval_ann_info is not None else None
+        out = []
+        for idx in range(len(labels)):
+            ds = Det3DDataSample(metainfo=dict(first.metainfo))
+            for k in first.keys():
+                if k not in ('gt_instances_3d', 'gt_occupancy_masks', 'eval_ann_info'):
+                    setattr(ds, k, getattr(first, k))
+            inst = InstanceData()
+            if boxes is not None:
+                inst.bboxes_3d = boxes[idx]
+            inst.labels_3d = labels[idx]
+            ds.gt_instances_3d = inst
+            if masks is not None:
+                ds.gt_occupancy_masks = masks[idx]
+            if 'eval_ann_info' in first:
+                ds.eval_ann_info = None if ann is None else dict(gt_bboxes_3d=ann['gt_bboxes_3d'][idx],
+                                                                 gt_labels_3d=ann['gt_labels_3d'][idx])
+            out.append(ds)
+        return out
+
     def forward(self, data: dict, training: bool = False) -> dict:
         inputs, data_samples = data['inputs'], data.get('data_samples')
+        if self.batchwise_inputs and data_samples is not None:
+            data_samples = self.split_batchwise(data_samples)
         dev = self.device
         out = {}
-        if 'points' in inputs:
-            out['points'] = [p.to(dev, non_blocking=True) for p in inputs['points']]
+        if 'points' in inputs:      # continuous inputs arrive pseudo-collated: points[idx] = [tensor] (batch size 1)
+            out['points'] = [[q.to(dev, non_blocking=True) for q in p] if isinstance(p, (list, tuple))
+                             else p.to(dev, non_blocking=True) for p in inputs['points']]
         if 'img' in inputs:
             imgs = inputs['img']
             if isinstance(imgs, torch.Tensor):                      # default_collate: one (B,[V,]3,H,W) tensor, one copy
@@ -75,7 +109,8 @@ class Det3DDataPreprocessor(nn.Module):
                      1 if self.channel_conversion else 0, 1, ptr(dst), _ffi.dtype_code(self.compute_dtype), stream())
             out['imgs'] = buf.view(B, V, Hp, Wp, 3).permute(0, 1, 4, 2, 3)   # (B,V,3,Hp,Wp), channels-last memory
             if data_samples is not None:
-                for ds, i in zip(data_samples, imgs):
+                per_sample = imgs if len(imgs) == len(data_samples) else [imgs[0]] * len(data_samples)
+                for ds, i in zip(data_samples, per_sample):       # batchwise: every prefix shares the scan's images
                     ds.set_metainfo({'batch_input_shape': (Hp, Wp),
                                      'pad_shape': (int(math.ceil(i.shape[-2] / d) * d),
                                                    int(math.ceil(i.shape[-1] / d) * d))})
@@ -218,6 +253,54 @@ class SparseFeatureFusionSingleStage3DDetector(nn.Module):
         return self(**data, mode='predict')
 
     test_step = val_step
+
+
+@MODELS.register_module()
+class Embodied3DDetector(SparseFeatureFusionSingleStage3DDetector):
+    """Continuous (1..N frames) detector (embodiedscan/models/detectors/embodied_det3d.py:90-207): the batch is ONE scan
+    seen through its N growing frame prefixes. Sample ``idx`` holds the points of frames 0..idx and is painted from the
+    image features of views 0..idx only; everything else is the multi-view detector. Same kernels: the sparse backbone
+    and the head see an N-sample batch, painting runs once per (prefix, level) on a view-prefix slice of the feature map
+    (the slice is contiguous, so no copy and no new kernel)."""
+
+    def __init__(self, *args, neck_lidar=None, **kwargs):
+        assert neck_lidar is None, 'no configured continuous model uses neck_lidar'
+        super().__init__(*args, **kwargs)
+
+    def extract_feat(self, batch_inputs_dict, batch_data_samples):
+        points = batch_inputs_dict['points']
+        assert all(isinstance(p, (list, tuple)) and len(p) == 1 for p in points), 'only support batch_size=1 for now!'
+        points = [p[0] for p in points]
+        img = batch_inputs_dict['imgs']
+        assert img.dim() == 5 and img.shape[0] == 1, 'one scan: (1, n_views, C, H, W)'
+        batch_img_metas = [ds.metainfo for ds in batch_data_samples]
+        n_prefix, V = len(points), img.shape[1]
+        assert n_prefix == len(batch_img_metas) <= V
+        img4 = img.reshape([-1] + list(img.shape)[2:]).to(self.compute_dtype)
+        if not img4.is_contiguous(memory_format=torch.channels_last):
+            img4 = img4.contiguous(memory_format=torch.channels_last)
+        img_features = self.backbone(img4)                               # per level (V, C, Hf, Wf)
+        coordinates, features = self.voxelize(points)
+        x = SP.SparseTensor(coordinates=coordinates, features=features.to(self.compute_dtype), batch_size=n_prefix)
+        x = self.backbone_3d(x)
+        dev = img.device
+        pad_hw = tuple(img.shape[-2:])
+        metas = [pack_paint_metas([m], dev) for m in batch_img_metas]
+        projs = [pack_projections([m], self.coord_type, dev) for m in batch_img_metas]       # (1, V, 4, 4) each
+        for level_idx in range(len(x)):
+            lv = x[level_idx]
+            feat = img_features[level_idx]
+            painted = lv.F.new_zeros((lv.F.shape[0], feat.shape[1]))
+            for idx, rows in enumerate(lv.decomposition_permutations):
+                if rows.numel() == 0:
+                    continue
+                c = lv.C[rows].clone()
+                c[:, 0] = 0                                              # one "scan" per launch: the prefix itself
+                out = paint_points(feat[:idx + 1], c.contiguous(), metas[idx], projs[idx][:, :idx + 1].contiguous(),
+                                   self.voxel_size, pad_hw, idx + 1)
+                painted = painted.index_copy(0, rows, out.to(painted.dtype))
+            x[level_idx] = lv.replace_feature(torch.cat([lv.F, painted], 1))
+        return x
 
 
 def parse_losses(losses: dict):

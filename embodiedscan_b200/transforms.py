@@ -171,3 +171,44 @@ class GlobalRotScaleTrans:
         return results
 
     transform = __call__
+
+
+@TRANSFORMS.register_module()
+class ConstructMultiSweeps:
+    """N aggregated frames -> the 1..N growing prefixes of the continuous setting (multiview.py:172-246):
+    ``points`` (tensor of all frames, frame order) + ``points_slice_indices`` -> list of N prefix clouds;
+    ``gt_bboxes_3d`` / ``gt_labels_3d`` -> per-prefix lists of the instances visible in any frame so far
+    (``visible_instance_masks``), ``visible_occupancy_masks`` -> cumulative ``gt_occupancy_masks``.
+    Prefix clouds are views into ONE buffer ordered by frame, so no point is copied N times."""
+
+    def __call__(self, results: dict) -> dict:
+        pts = results['points']
+        pts = pts.tensor if hasattr(pts, 'tensor') else pts
+        sl = results['points_slice_indices']
+        n = len(sl) - 1
+        results['points'] = [pts[sl[0]:sl[i + 1]] for i in range(n)]
+        if 'visible_instance_masks' in results:
+            boxes, labels = results['gt_bboxes_3d'], results['gt_labels_3d']
+            seen = set()
+            out_b, out_l = [], []
+            for i in range(n):
+                seen |= set(np.argwhere(np.array(results['visible_instance_masks'][i])).flatten().tolist())
+                idx = np.array(list(seen), dtype=np.int32)       # the reference's set -> list order, kept on purpose
+                out_b.append(boxes[torch.as_tensor(idx, dtype=torch.long)])
+                out_l.append(labels[idx])
+            results['gt_bboxes_3d'], results['gt_labels_3d'] = out_b, out_l
+            if 'eval_ann_info' in results:
+                results['eval_ann_info']['gt_bboxes_3d'] = out_b
+                results['eval_ann_info']['gt_labels_3d'] = out_l
+        if 'visible_occupancy_masks' in results:
+            cum, out_m = None, []
+            for i in range(n):
+                m = np.asarray(results['visible_occupancy_masks'][i])
+                cum = m if cum is None else np.logical_or(cum, m)
+                out_m.append(cum)
+            results['gt_occupancy_masks'] = out_m
+            if 'eval_ann_info' in results:
+                results['eval_ann_info']['gt_occupancy_masks'] = out_m
+        return results
+
+    transform = __call__

@@ -314,8 +314,11 @@ def predict_single(center_preds, bbox_preds, cls_preds, points, nms_pre=1000, sc
 
 
 # ------------------------------------------------------------------------------------------------ whole detector
-def extract_feat(sd, cfg, points: List[torch.Tensor], imgs: torch.Tensor, img_metas: List[dict], training: bool):
-    """sparse_featfusion_single_stage.py:86-221. imgs (B,V,3,Hp,Wp) normalised fp32."""
+def extract_feat(sd, cfg, points: List[torch.Tensor], imgs: torch.Tensor, img_metas: List[dict], training: bool,
+                 continuous: bool = False):
+    """sparse_featfusion_single_stage.py:86-221. imgs (B,V,3,Hp,Wp) normalised fp32.
+    continuous=True restates embodied_det3d.py:90-207 instead: imgs (1,V,...) of ONE scan, `points[b]` = its frames
+    0..b, and sample b is painted from views 0..b only (:146-149)."""
     vs = cfg['bbox_head']['voxel_size']
     cache = {}
     coords = np.concatenate([S.voxelize(p, vs, b) for b, p in enumerate(points)], 0)
@@ -330,23 +333,24 @@ def extract_feat(sd, cfg, points: List[torch.Tensor], imgs: torch.Tensor, img_me
     f2d = resnet2d(sd, 'backbone.', cfg['backbone']['depth'], imgs.reshape((-1, ) + tuple(imgs.shape[2:])))
     pad_hw = tuple(imgs.shape[-2:])
     for li, lv in enumerate(levels):
-        fl = f2d[li].reshape((B, V) + tuple(f2d[li].shape[1:]))
+        fl = f2d[li].reshape((imgs.shape[0], V) + tuple(f2d[li].shape[1:]))
         painted = torch.zeros((lv.coords.shape[0], fl.shape[2]))
         for b in range(B):
             sel = np.nonzero(lv.coords[:, 0] == b)[0]
             pm = img_metas[b]['depth2img']
+            nv = b + 1 if continuous else V
             proj = torch.from_numpy(np.stack([compose_projection(pm['intrinsic'][v], pm['extrinsic'][v])
-                                              for v in range(V)]))
+                                              for v in range(nv)]))
             pts = torch.from_numpy(lv.coords[sel, 1:]).to(torch.int32) * vs
-            out, _ = batch_point_sample(img_metas[b], fl[b], pts, proj, pad_hw)
+            out, _ = batch_point_sample(img_metas[b], fl[0][:nv] if continuous else fl[b], pts, proj, pad_hw)
             painted = painted.index_copy(0, torch.from_numpy(sel), out)
         lv.F = torch.cat([lv.F, painted], 1)
     return levels, cache
 
 
-def detector_loss(sd, cfg, points, imgs, data_samples, world_n_pos=None) -> Dict[str, torch.Tensor]:
+def detector_loss(sd, cfg, points, imgs, data_samples, world_n_pos=None, continuous=False) -> Dict[str, torch.Tensor]:
     metas = [d.metainfo for d in data_samples]
-    levels, cache = extract_feat(sd, cfg, points, imgs, metas, True)
+    levels, cache = extract_feat(sd, cfg, points, imgs, metas, True, continuous)
     B = len(points)
     outs = head_forward(sd, 'bbox_head.', levels, cfg['bbox_head']['voxel_size'], B, True, cache,
                         cfg['bbox_head']['pts_prune_threshold'])
@@ -361,9 +365,9 @@ def detector_loss(sd, cfg, points, imgs, data_samples, world_n_pos=None) -> Dict
     return dict(loss_center=torch.stack(cl).mean(), loss_bbox=torch.stack(bl).mean(), loss_cls=torch.stack(kl).mean())
 
 
-def detector_predict(sd, cfg, points, imgs, data_samples):
+def detector_predict(sd, cfg, points, imgs, data_samples, continuous=False):
     metas = [d.metainfo for d in data_samples]
-    levels, cache = extract_feat(sd, cfg, points, imgs, metas, False)
+    levels, cache = extract_feat(sd, cfg, points, imgs, metas, False, continuous)
     B = len(points)
     outs = head_forward(sd, 'bbox_head.', levels, cfg['bbox_head']['voxel_size'], B, False, cache,
                         cfg['bbox_head']['pts_prune_threshold'])

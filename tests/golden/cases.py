@@ -186,3 +186,30 @@ def augment_inputs():
     s = synth_scan(5, n_views=2, H=48, W=64, n_points=500)
     boxes = s['data_sample'].gt_instances_3d.bboxes_3d.tensor.clone()
     return s['points'].clone(), boxes, 2
+
+
+def continuous_inputs(scan=7, n_views=3, per_view=500):
+    """One scan as the continuous pipeline sees it before ConstructMultiSweeps: frame-ordered points with slice indices
+    (AggregateMultiViewPoints(save_slices=True)), per-frame visibility of the GT instances, images, GT."""
+    from embodiedscan_b200.synth import synth_scan
+    from oracle import data_ref as D
+    s = synth_scan(scan, n_views=n_views, H=240, W=320, n_points=200)
+    meta = s['data_sample'].metainfo
+    pm = meta['depth2img']
+    g = torch.Generator().manual_seed(100 + scan)
+    allp, counts = D.unproject_depth(s['depth'], pm['intrinsic'], pm['extrinsic'])
+    chunks, off = [], 0
+    for c in counts.tolist():
+        p = division_safe(allp[off:off + c])
+        chunks.append(p[torch.randperm(p.shape[0], generator=g)[:per_view]])
+        off += c
+    sl = [0]
+    for c in chunks:
+        sl.append(sl[-1] + c.shape[0])
+    gt = s['data_sample'].gt_instances_3d
+    n_box = len(gt.bboxes_3d)
+    vis = torch.rand(n_views, n_box, generator=g) < 0.4
+    vis[0, :3] = True
+    return dict(points=torch.cat(chunks).contiguous(), points_slice_indices=sl, img=s['img'], meta=meta,
+                boxes=gt.bboxes_3d.tensor.clone(), labels=gt.labels_3d.clone(),
+                visible_instance_masks=[v.tolist() for v in vis])

@@ -189,6 +189,13 @@ class BaseDataElement:
     def new(self, **k):
         return type(self)(metainfo=self.metainfo)
 
+    def clone(self):
+        out = type(self)(metainfo=dict(self.metainfo))
+        for k in self._data_fields:
+            object.__setattr__(out, k, getattr(self, k))
+            out._data_fields.add(k)
+        return out
+
 
 class InstanceData(BaseDataElement):
     def __len__(self):

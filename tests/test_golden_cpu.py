@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import (HashTextEncoder, augment_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
+from cases import (HashTextEncoder, augment_inputs, continuous_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
                    target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_state_dict  # noqa: E402
 
@@ -387,3 +387,73 @@ def test_device_augmentations_match_reference():
     meta['pcd_rotation'] = torch.as_tensor(d['pcd_rotation']).numpy()
     back = M.apply_3d_transformation_reverse(d['points'], meta)
     assert float((back - pts).abs().max()) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ continuous (f4)
+CONT_WATCH = {'bbox_head.conv_cls.kernel': None, 'bbox_head.conv_reg.kernel': None, 'backbone_3d.conv1.kernel': None,
+              'backbone.layer2.0.conv1.weight': 'backbone.layer2.0.cb1.conv.weight',
+              'backbone.layer4.0.conv1.weight': 'backbone.layer4.0.cb1.conv.weight'}
+
+
+def continuous_batch(scan=7):
+    """The product's own continuous front-end: ConstructMultiSweeps -> one data sample with per-prefix lists, in the
+    pseudo-collated layout a batch-size-1 dataloader hands to the model."""
+    from embodiedscan_b200.structures import Det3DDataSample, EulerDepthInstance3DBoxes, InstanceData
+    from embodiedscan_b200.transforms import ConstructMultiSweeps
+    ci = continuous_inputs(scan)
+    res = ConstructMultiSweeps()(dict(points=ci['points'].clone(), points_slice_indices=ci['points_slice_indices'],
+                                      gt_bboxes_3d=EulerDepthInstance3DBoxes(ci['boxes'].clone(), box_dim=9),
+                                      gt_labels_3d=ci['labels'].clone(),
+                                      visible_instance_masks=ci['visible_instance_masks']))
+    ds = Det3DDataSample(metainfo=dict(ci['meta']))
+    gt = InstanceData()
+    gt.bboxes_3d, gt.labels_3d = res['gt_bboxes_3d'], res['gt_labels_3d']
+    ds.gt_instances_3d = gt
+    ds.eval_ann_info = None
+    return dict(inputs=dict(points=[[p] for p in res['points']], img=[ci['img']]), data_samples=[ds]), res
+
+
+def continuous_config():
+    cfg = det_config()
+    cfg['type'] = 'Embodied3DDetector'
+    cfg['data_preprocessor'] = dict(cfg['data_preprocessor'], batchwise_inputs=True)
+    return cfg
+
+
+def test_continuous_front_end_matches_reference():
+    from embodiedscan_b200.detectors import Det3DDataPreprocessor
+    g = load('continuous_det')
+    data, res = continuous_batch()
+    assert [len(p) for p in res['points']] == g['sweep_sizes'].tolist()
+    assert [len(l) for l in res['gt_labels_3d']] == g['sweep_gt_counts'].tolist()
+    assert np.asarray(res['gt_labels_3d'][-1]).tolist() == g['sweep_gt_labels_last'].tolist()
+    assert res['points'][1].data_ptr() == res['points'][0].data_ptr(), 'prefixes are views into one buffer'
+    split = Det3DDataPreprocessor.split_batchwise(data['data_samples'])
+    assert len(split) == 3 and [len(s.gt_instances_3d.bboxes_3d) for s in split] == g['sweep_gt_counts'].tolist()
+    assert all(s.metainfo['depth2img'] is data['data_samples'][0].metainfo['depth2img'] for s in split)
+
+
+def test_continuous_detector_loss_and_gradients_match_reference():
+    from oracle import model_ref as M
+    g = load('continuous_det')
+    cfg = continuous_config()
+    _, sd = product_state_dict(cfg, g, adjust_fcaf3d_head)
+    from embodiedscan_b200.detectors import Det3DDataPreprocessor
+    data, res = continuous_batch()
+    samples = Det3DDataPreprocessor.split_batchwise(data['data_samples'])
+    imgs = M.preprocess_imgs(torch.stack(data['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    for ref_name, own in CONT_WATCH.items():
+        k = own or ref_name
+        sd[k] = sd[k].clone().requires_grad_(True)
+    out = M.detector_loss(sd, cfg, list(res['points']), imgs, samples, continuous=True)
+    sum(out.values()).backward()
+    for k in ('loss_center', 'loss_bbox', 'loss_cls'):
+        assert rel(out[k], g['a_' + k]) <= 2e-5, (k, float(out[k]), float(g['a_' + k]))
+    for ref_name, own in CONT_WATCH.items():
+        grad = sd[own or ref_name].grad
+        want = torch.from_numpy(g[f'a_grad/{ref_name}'])
+        got = sampled(grad).reshape(want.shape)
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 2e-4 * scale, (ref_name, float((got - want).abs().max()), scale)
+        assert rel(grad.double().norm(), g[f'a_gradnorm/{ref_name}']) <= 5e-4, ref_name

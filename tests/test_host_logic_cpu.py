@@ -55,3 +55,73 @@ def test_preprocessor_batching_and_padding(monkeypatch):
         assert len(calls) == 1 and calls[0][1:] == (40, 50, 64, 64)
         assert torch.equal(out, R.preprocess_multiview(ref, MEAN, STD))
         assert out.shape[2] == 3 and out.stride(2) == 1, 'channels-last memory under a (B,V,3,H,W) view'
+
+
+def test_preprocessor_batchwise_continuous_inputs(monkeypatch):
+    """batchwise_inputs=True: one scan with per-prefix annotation lists -> N samples, nested point lists kept."""
+    import embodiedscan_b200.detectors as D
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_golden_cpu import continuous_batch
+    calls = []
+    monkeypatch.setattr(D, 'call', _emulated_img_normalize(calls))
+    monkeypatch.setattr(D, 'stream', lambda: None)
+    pre = D.Det3DDataPreprocessor(mean=MEAN, std=STD, bgr_to_rgb=True, pad_size_divisor=32, batchwise_inputs=True)
+    data, res = continuous_batch()
+    out = pre(data, True)
+    assert len(out['data_samples']) == 3 and len(calls) == 1
+    assert out['inputs']['imgs'].shape == (1, 3, 3, 256, 320)
+    assert [len(p) == 1 and p[0].shape[0] for p in out['inputs']['points']] == [500, 1000, 1500]
+    assert all(s.metainfo['pad_shape'] == (256, 320) for s in out['data_samples'])
+    assert [len(s.gt_instances_3d.labels_3d) for s in out['data_samples']] == [len(l) for l in res['gt_labels_3d']]
+
+
+def test_continuous_detector_view_prefix_painting_control_flow(monkeypatch):
+    """Embodied3DDetector.extract_feat with the CUDA pieces replaced by recorders: sample idx must be painted from the
+    contiguous view-prefix slice feat[:idx+1] with its own meta / projection prefix, rows scattered back in place."""
+    import types
+
+    import embodiedscan_b200.detectors as D
+
+    class FakeST:
+        def __init__(self, C, F, nb):
+            self.C, self.F, self.nb = C, F, nb
+
+        @property
+        def decomposition_permutations(self):
+            return [torch.nonzero(self.C[:, 0] == b).squeeze(1) for b in range(self.nb)]
+
+        def replace_feature(self, f):
+            return FakeST(self.C, f, self.nb)
+
+    g = torch.Generator().manual_seed(0)
+    n_prefix, V = 3, 3
+    coords = torch.cat([torch.cat([torch.full((n, 1), b), torch.randint(0, 50, (n, 3), generator=g)], 1)
+                        for b, n in enumerate((4, 0, 6))]).int()
+    coords = coords[torch.randperm(coords.shape[0], generator=g)]            # interleaved rows, one empty prefix
+    feats3d = torch.randn(coords.shape[0], 5, generator=g)
+    levels = [FakeST(coords, feats3d, n_prefix)]
+    calls = []
+
+    def fake_paint(feat, c, metas, proj, voxel_size, pad_hw, n_views):
+        assert feat.is_contiguous(memory_format=torch.channels_last) and feat.shape[0] == n_views
+        assert proj.shape == (1, n_views, 4, 4) and proj.is_contiguous() and int(c[:, 0].abs().sum()) == 0
+        calls.append((n_views, c.shape[0], int(metas[0])))
+        return torch.full((c.shape[0], feat.shape[1]), float(n_views))
+    monkeypatch.setattr(D, 'paint_points', fake_paint)
+    monkeypatch.setattr(D, 'pack_paint_metas', lambda ms, dev: torch.tensor([ms[0]['tag']]))
+    monkeypatch.setattr(D, 'pack_projections', lambda ms, ct, dev: torch.zeros(1, V, 4, 4))
+    monkeypatch.setattr(D.SP, 'SparseTensor', lambda **kw: None)
+    det = D.Embodied3DDetector.__new__(D.Embodied3DDetector)
+    torch.nn.Module.__init__(det)
+    det.compute_dtype, det.voxel_size, det.coord_type = torch.float32, 0.01, 'DEPTH'
+    det.backbone = lambda x: [torch.randn(V, 7, 4, 6).contiguous(memory_format=torch.channels_last)]
+    det.backbone_3d = lambda x: levels
+    det.voxelize = lambda pts: (torch.zeros(1, 4, dtype=torch.int32), torch.zeros(1, 3))
+    samples = [types.SimpleNamespace(metainfo=dict(tag=10 + i)) for i in range(n_prefix)]
+    out = det.extract_feat(dict(points=[[torch.zeros(2, 3)] for _ in range(n_prefix)],
+                                imgs=torch.zeros(1, V, 3, 32, 32)), samples)
+    assert calls == [(1, 4, 10), (3, 6, 12)], calls                          # the empty prefix launches nothing
+    f = out[0].F
+    assert f.shape == (coords.shape[0], 5 + 7) and torch.equal(f[:, :5], feats3d)
+    want = torch.tensor([1., 0., 3.])[coords[:, 0].long()]
+    assert torch.equal(f[:, 5:], want[:, None].expand(-1, 7))

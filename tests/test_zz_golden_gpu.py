@@ -212,3 +212,27 @@ def test_grounder_predictions_match_reference():
         want_s, want_b = torch.from_numpy(g[f'p_scores_{b}']), torch.from_numpy(g[f'p_boxes_{b}'])
         assert float((ds.pred_instances_3d.scores_3d.cpu() - want_s).abs().max()) <= 1e-3
         assert float((ds.pred_instances_3d.bboxes_3d.tensor.cpu() - want_b).abs().max()) <= 1e-3 * float(want_b.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ continuous (f4)
+def test_continuous_detector_loss_and_gradients_match_reference():
+    from test_golden_cpu import CONT_WATCH, continuous_batch, continuous_config
+    g = load('continuous_det')
+    cfg = continuous_config()
+    model, _ = product_state_dict(cfg, g, adjust_fcaf3d_head)
+    model = model.to(DEV).train()
+    data, _ = continuous_batch()
+    data = model.data_preprocessor(data, True)
+    assert len(data['data_samples']) == 3
+    losses = model(**data, mode='loss')
+    sum(losses.values()).backward()
+    for k in ('loss_center', 'loss_bbox', 'loss_cls'):
+        assert rel(losses[k], g['a_' + k]) <= 1e-3, (k, float(losses[k]), float(g['a_' + k]))
+    params = dict(model.named_parameters())
+    for ref_name, own in CONT_WATCH.items():
+        grad = params[own or ref_name].grad.detach().cpu()
+        want = torch.from_numpy(g[f'a_grad/{ref_name}'])
+        got = sampled(grad).reshape(want.shape)
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 2e-3 * scale, (ref_name, float((got - want).abs().max()), scale)
+        assert rel(grad.double().norm(), g[f'a_gradnorm/{ref_name}']) <= 2e-3, ref_name
