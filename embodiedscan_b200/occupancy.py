@@ -347,6 +347,23 @@ class DenseFusionOccPredictor(nn.Module):
         fused = torch.cat([img_volume.to(self.compute_dtype), point_volume], dim=1)
         return self.neck_3d(fused.contiguous(memory_format=torch.channels_last_3d)), valid_preds.float()
 
+    def sparse_volume(self, points, prior):
+        """MinkResNet over the clamped voxel grid -> dense (B, C, X, Y, Z) volume of its coarsest level."""
+        dev = prior.device
+        vs = prior.new_tensor(self.voxel_size)
+        lo = prior.new_tensor(self.point_cloud_range[:3])
+        coords, feats = [], []
+        for b, p in enumerate(points):
+            q = torch.floor((p[:, :3].float() - lo) / vs).to(torch.int32)
+            hi = torch.tensor([n * self.voxel_stride - 1 for n in self.n_voxels], dtype=torch.int32, device=dev)
+            q = torch.minimum(torch.clamp(q, min=0), hi)
+            coords.append(torch.cat([torch.full((q.shape[0], 1), b, dtype=torch.int32, device=dev), q], 1))
+            feats.append(p.float() if self.use_xyz_feat else p[:, 3:].float())
+        x = SP.SparseTensor(coordinates=torch.cat(coords), features=torch.cat(feats).to(self.compute_dtype),
+                            batch_size=len(points))
+        last = self.backbone_3d(x)[-1]
+        return last.dense((len(points), last.F.shape[-1], *self.n_voxels), min_coordinate=[0, 0, 0])[0]
+
     def loss(self, batch_inputs_dict, batch_data_samples, **kwargs):
         x, valid = self.extract_feat(batch_inputs_dict, batch_data_samples)
         return self.bbox_head.loss(x, batch_data_samples)
@@ -384,3 +401,42 @@ class DenseFusionOccPredictor(nn.Module):
         return self(**data, mode='predict')
 
     test_step = val_step
+
+
+@MODELS.register_module()
+class EmbodiedOccPredictor(DenseFusionOccPredictor):
+    """Continuous (1..N frames) occupancy predictor (embodiedscan/models/detectors/embodied_occ.py:118-247): the batch is
+    ONE scan seen through its N growing frame prefixes; prefix ``idx`` paints the prior grid from views 0..idx only and
+    voxelises the points of frames 0..idx. Same kernels as the multi-view predictor; painting runs once per prefix on a
+    contiguous view-prefix slice of the FPN map."""
+
+    def extract_feat(self, batch_inputs_dict, batch_data_samples):
+        img = batch_inputs_dict['imgs']
+        metas_list = [ds.metainfo for ds in batch_data_samples]
+        assert img.dim() == 5 and img.shape[0] == 1, 'one scan: (1, n_views, C, H, W)'
+        V, dev = img.shape[1], img.device
+        n_prefix = len(metas_list)
+        assert n_prefix <= V
+        img4 = img.reshape([-1] + list(img.shape)[2:]).to(self.compute_dtype)
+        if not img4.is_contiguous(memory_format=torch.channels_last):
+            img4 = img4.contiguous(memory_format=torch.channels_last)
+        feat2d = self.neck(self.backbone(img4))[0]                      # (V, C, H/4, W/4)
+        if not feat2d.is_contiguous(memory_format=torch.channels_last):
+            feat2d = feat2d.contiguous(memory_format=torch.channels_last)
+        prior = self.prior_generator.grid_anchors([self.n_voxels[::-1]], device=dev)[0][:, :3]
+        if 'origin' in metas_list[0]['depth2img']:
+            prior = prior + prior.new_tensor(np.asarray(metas_list[0]['depth2img']['origin'], dtype=np.float32))
+        prior = prior.contiguous()
+        vols = []
+        for idx, meta in enumerate(metas_list):
+            proj = pack_projections([meta], self.coord_type, dev)[:, :idx + 1].contiguous()
+            vol = paint_float_points(feat2d[:idx + 1], prior, None, pack_paint_metas([meta], dev), proj,
+                                     tuple(img.shape[-2:]), idx + 1)
+            vols.append(vol.view(self.n_voxels[::-1] + [-1]).permute(3, 2, 1, 0))
+        img_volume = torch.stack(vols)                                   # (N, C, X, Y, Z)
+        valid_preds = ~torch.all(img_volume == 0, dim=1, keepdim=True)
+        points = batch_inputs_dict['points']
+        assert all(isinstance(p, (list, tuple)) and len(p) == 1 for p in points), 'only support batch_size=1 for now!'
+        point_volume = self.sparse_volume([p[0] for p in points], prior)
+        fused = torch.cat([img_volume.to(self.compute_dtype), point_volume], dim=1)
+        return self.neck_3d(fused.contiguous(memory_format=torch.channels_last_3d)), valid_preds.float()

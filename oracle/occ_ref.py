@@ -77,22 +77,28 @@ def imvoxel_neck(sd, prefix, x, n_blocks, training):
     return outs[::-1]
 
 
-def extract_feat(sd, cfg, points: List[torch.Tensor], imgs: torch.Tensor, img_metas: List[dict], training: bool):
+def extract_feat(sd, cfg, points: List[torch.Tensor], imgs: torch.Tensor, img_metas: List[dict], training: bool,
+                 continuous: bool = False):
+    """dense_fusion_occ.py:120-259; continuous=True restates embodied_occ.py:118-247 (one scan, `points[b]` = frames
+    0..b, sample b painted from views 0..b)."""
     B, V = imgs.shape[:2]
+    if continuous:
+        B = len(points)
     n_voxels = list(cfg['n_voxels'])
     pr = cfg['prior_generator']['ranges'][0]
     f2d = M.resnet2d(sd, 'backbone.', cfg['backbone']['depth'], imgs.reshape((-1, ) + tuple(imgs.shape[2:])))
     f0 = fpn(sd, 'neck.', f2d)[0]
-    f0 = f0.reshape((B, V) + tuple(f0.shape[1:]))
+    f0 = f0.reshape((imgs.shape[0], V) + tuple(f0.shape[1:]))
     prior = prior_points(pr, n_voxels)
     pad_hw = tuple(imgs.shape[-2:])
     vols = []
     for b in range(B):
         pm = img_metas[b]['depth2img']
         pts = prior + torch.as_tensor(np.asarray(pm['origin'], dtype=np.float32)) if 'origin' in pm else prior
+        nv = b + 1 if continuous else V
         proj = torch.from_numpy(np.stack([M.compose_projection(pm['intrinsic'][v], pm['extrinsic'][v])
-                                          for v in range(V)]))
-        vol, _ = M.batch_point_sample(img_metas[b], f0[b], pts, proj, pad_hw)
+                                          for v in range(nv)]))
+        vol, _ = M.batch_point_sample(img_metas[b], f0[0][:nv] if continuous else f0[b], pts, proj, pad_hw)
         vols.append(vol.reshape(n_voxels[::-1] + [-1]).permute(3, 2, 1, 0))
     img_volume = torch.stack(vols)
 
@@ -121,11 +127,14 @@ def extract_feat(sd, cfg, points: List[torch.Tensor], imgs: torch.Tensor, img_me
     return imvoxel_neck(sd, 'neck_3d.', fused, cfg['neck_3d']['n_blocks'], training)
 
 
-def multiscale_gt(gt_occ: List[torch.Tensor], ratio, shape) -> torch.Tensor:
+def multiscale_gt(gt_occ: List[torch.Tensor], ratio, shape, masks=None) -> torch.Tensor:
+    """occ_loss.py:7-37; `masks[i]` (X,Y,Z) bool at THIS scale: invisible voxels become 255 (ignored)."""
     gt = torch.zeros([shape[0], shape[2], shape[3], shape[4]], dtype=torch.long)
     for i in range(gt.shape[0]):
         for row in gt_occ[i].tolist():
             gt[i, row[0] // ratio, row[1] // ratio, row[2] // ratio] = row[3]
+        if masks is not None:
+            gt[i][~masks[i]] = 255
     return gt
 
 
@@ -170,13 +179,17 @@ def sem_scal_loss(pred, tgt):
     return loss / count
 
 
-def occ_loss(sd, cfg, points, imgs, data_samples) -> Dict[str, torch.Tensor]:
-    feats = extract_feat(sd, cfg, points, imgs, [d.metainfo for d in data_samples], True)
+def occ_loss(sd, cfg, points, imgs, data_samples, continuous=False) -> Dict[str, torch.Tensor]:
+    feats = extract_feat(sd, cfg, points, imgs, [d.metainfo for d in data_samples], True, continuous)
     gt_occ = [d.gt_occupancy.cpu() for d in data_samples]
+    masks = [torch.as_tensor(d.gt_occupancy_masks).cpu() for d in data_samples] \
+        if 'gt_occupancy_masks' in data_samples[0] else None
     out = {}
     for i, f in enumerate(feats):
         pred = F.conv3d(f, sd[f'bbox_head.occ.{i}.weight'])
-        gt = multiscale_gt(gt_occ, 2 ** i, pred.shape)
+        pooled = None if masks is None else [F.max_pool3d(m.float()[None], 2 ** i, stride=2 ** i)[0].bool()
+                                             for m in masks]           # imvoxel_occ_head.py:150-156
+        gt = multiscale_gt(gt_occ, 2 ** i, pred.shape, pooled)
         li = F.cross_entropy(pred, gt, ignore_index=255) + sem_scal_loss(pred, gt) + geo_scal_loss(pred, gt)
         out[f'loss_occ_{i}'] = li * 0.5 ** i
     return out

@@ -213,3 +213,20 @@ def continuous_inputs(scan=7, n_views=3, per_view=500):
     return dict(points=torch.cat(chunks).contiguous(), points_slice_indices=sl, img=s['img'], meta=meta,
                 boxes=gt.bboxes_3d.tensor.clone(), labels=gt.labels_3d.clone(),
                 visible_instance_masks=[v.tolist() for v in vis])
+
+
+def continuous_occ_inputs(scan=8, n_views=3, per_view=1200):
+    """continuous_inputs + occupancy ground truth and per-frame visibility masks of the 8x8x4 grid."""
+    from embodiedscan_b200.synth import synth_occupancy
+    cfg = occ_config()
+    ci = continuous_inputs(scan, n_views, per_view)
+    ds = type('DS', (), {})()
+    from embodiedscan_b200.structures import EulerDepthInstance3DBoxes, InstanceData
+    gt = InstanceData()
+    gt.bboxes_3d = EulerDepthInstance3DBoxes(ci['boxes'], box_dim=9)
+    gt.labels_3d = ci['labels']
+    ds.gt_instances_3d = gt
+    ci['gt_occupancy'] = synth_occupancy(ds, cfg['point_cloud_range'], cfg['n_voxels'])
+    g = torch.Generator().manual_seed(300 + scan)
+    ci['visible_occupancy_masks'] = [(torch.rand(*cfg['n_voxels'], generator=g) < 0.45).numpy() for _ in range(n_views)]
+    return ci

@@ -28,7 +28,7 @@ import refstubs  # noqa: E402
 
 refstubs.install()
 
-from cases import (HashTextEncoder, augment_inputs, continuous_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs,  # noqa: E402
+from cases import (HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs,  # noqa: E402
                    preprocess_inputs, target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_tensor  # noqa: E402
 
@@ -479,7 +479,69 @@ def gen_continuous():
     save('continuous_det', **out)
 
 
-GENERATORS = dict(continuous=gen_continuous, augment=gen_augment, grounding=gen_grounding, detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions,
+def gen_continuous_occ():
+    """f4: ConstructMultiSweeps (visible_occupancy_masks branch) -> batchwise preprocessor -> EmbodiedOccPredictor
+    (embodied_occ.py) -> ImVoxelOccHead.loss with per-prefix visibility masks (imvoxel_occ_head.py:145-168)."""
+    import copy
+
+    import embodiedscan.models  # noqa: F401
+    from embodiedscan.datasets.transforms.multiview import ConstructMultiSweeps
+    from embodiedscan.models.data_preprocessors.data_preprocessor import Det3DDataPreprocessor
+    from embodiedscan.registry import MODELS
+    from embodiedscan.structures import EulerDepthInstance3DBoxes
+    from embodiedscan.utils.typing_config import Det3DDataElement
+    from mmengine.structures import InstanceData
+    cfg = occ_config()
+    c = copy.deepcopy(cfg)
+    c['type'] = 'EmbodiedOccPredictor'
+    c.pop('data_preprocessor')
+    model = MODELS.build(_config_dict(c))
+    manifest = fill_module(model)
+    out = manifest_arrays(manifest)
+    pre = Det3DDataPreprocessor(mean=cfg['data_preprocessor']['mean'], std=cfg['data_preprocessor']['std'],
+                                bgr_to_rgb=True, pad_size_divisor=32, batchwise_inputs=True)
+
+    def inputs(scan):
+        ci = continuous_occ_inputs(scan)
+        res = ConstructMultiSweeps().transform(dict(
+            points=type('P', (), dict(tensor=ci['points'].clone()))(), points_slice_indices=ci['points_slice_indices'],
+            gt_bboxes_3d=EulerDepthInstance3DBoxes(ci['boxes'].clone(), box_dim=9, origin=(.5, .5, .5)),
+            gt_labels_3d=ci['labels'].numpy().copy(), visible_instance_masks=ci['visible_instance_masks'],
+            visible_occupancy_masks=ci['visible_occupancy_masks']))
+        meta = dict(ci['meta'])
+        meta['box_type_3d'] = EulerDepthInstance3DBoxes
+        ds = Det3DDataElement(metainfo=meta)
+        gt = InstanceData()
+        gt.bboxes_3d = res['gt_bboxes_3d']
+        gt.labels_3d = [torch.from_numpy(np.asarray(l)) for l in res['gt_labels_3d']]
+        ds.gt_instances_3d = gt
+        ds.gt_occupancy = ci['gt_occupancy'].clone()
+        ds.gt_occupancy_masks = [torch.from_numpy(np.asarray(m)) for m in res['gt_occupancy_masks']]
+        ds.eval_ann_info = None
+        data = pre.simple_process(dict(inputs=dict(points=[[p] for p in res['points']], img=[ci['img']]),
+                                       data_samples=[ds]), True)
+        return data, res
+    data, res = inputs(8)
+    out['mask_counts'] = np.array([int(np.asarray(m).sum()) for m in res['gt_occupancy_masks']])
+    calib = calibrate_norms(model, lambda: model(data['inputs'], data['data_samples'], mode='loss'))
+    out.update(calib)
+    model.train()
+    data, _ = inputs(8)
+    losses = model(data['inputs'], data['data_samples'], mode='loss')
+    sum(losses.values()).backward()
+    for k, v in losses.items():
+        out['a_' + k] = v
+    params = dict(model.named_parameters())
+    for k in ('bbox_head.occ.0.weight', 'bbox_head.occ.2.weight', 'neck.lateral_convs.0.conv.weight'):
+        g = params[k].grad
+        out[f'a_grad/{k}'] = g if g.numel() <= 4096 else g.flatten()[:: max(g.numel() // 4096, 1)][:4096]
+        out[f'a_gradnorm/{k}'] = g.double().norm()
+    print('continuous occ: mask counts', out['mask_counts'].tolist(), 'losses',
+          {k: round(float(v.detach()), 5) for k, v in losses.items()})
+    save('continuous_occ', **out)
+
+
+GENERATORS = dict(continuous_occ=gen_continuous_occ, continuous=gen_continuous, augment=gen_augment, grounding=gen_grounding, detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions,
                   eval=gen_eval)
 
 if __name__ == '__main__':

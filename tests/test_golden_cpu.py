@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import (HashTextEncoder, augment_inputs, continuous_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
+from cases import (HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
                    target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_state_dict  # noqa: E402
 
@@ -457,3 +457,61 @@ def test_continuous_detector_loss_and_gradients_match_reference():
         scale = float(want.abs().max())
         assert float((got - want).abs().max()) <= 2e-4 * scale, (ref_name, float((got - want).abs().max()), scale)
         assert rel(grad.double().norm(), g[f'a_gradnorm/{ref_name}']) <= 5e-4, ref_name
+
+
+def continuous_occ_batch(scan=8):
+    from embodiedscan_b200.structures import Det3DDataSample, EulerDepthInstance3DBoxes, InstanceData
+    from embodiedscan_b200.transforms import ConstructMultiSweeps
+    ci = continuous_occ_inputs(scan)
+    res = ConstructMultiSweeps()(dict(points=ci['points'].clone(), points_slice_indices=ci['points_slice_indices'],
+                                      gt_bboxes_3d=EulerDepthInstance3DBoxes(ci['boxes'].clone(), box_dim=9),
+                                      gt_labels_3d=ci['labels'].clone(),
+                                      visible_instance_masks=ci['visible_instance_masks'],
+                                      visible_occupancy_masks=ci['visible_occupancy_masks']))
+    ds = Det3DDataSample(metainfo=dict(ci['meta']))
+    gt = InstanceData()
+    gt.bboxes_3d, gt.labels_3d = res['gt_bboxes_3d'], res['gt_labels_3d']
+    ds.gt_instances_3d = gt
+    ds.gt_occupancy = ci['gt_occupancy'].clone()
+    ds.gt_occupancy_masks = [torch.from_numpy(np.asarray(m)) for m in res['gt_occupancy_masks']]
+    ds.eval_ann_info = None
+    return dict(inputs=dict(points=[[p] for p in res['points']], img=[ci['img']]), data_samples=[ds]), res
+
+
+def continuous_occ_config():
+    cfg = occ_config()
+    cfg['type'] = 'EmbodiedOccPredictor'
+    cfg['data_preprocessor'] = dict(cfg['data_preprocessor'], batchwise_inputs=True)
+    return cfg
+
+
+OCC_CONT_WATCH = ('bbox_head.occ.0.weight', 'bbox_head.occ.2.weight', 'neck.lateral_convs.0.conv.weight')
+
+
+def test_continuous_occupancy_loss_and_gradients_match_reference():
+    from embodiedscan_b200.detectors import Det3DDataPreprocessor
+    from oracle import model_ref as M
+    from oracle import occ_ref as R
+    g = load('continuous_occ')
+    cfg = continuous_occ_config()
+    _, sd = product_state_dict(cfg, g, lambda s: s)
+    data, res = continuous_occ_batch()
+    assert [int(np.asarray(m).sum()) for m in res['gt_occupancy_masks']] == g['mask_counts'].tolist()
+    samples = Det3DDataPreprocessor.split_batchwise(data['data_samples'])
+    assert [int(s.gt_occupancy_masks.sum()) for s in samples] == g['mask_counts'].tolist()
+    imgs = M.preprocess_imgs(torch.stack(data['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    for k in OCC_CONT_WATCH:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    out = R.occ_loss(sd, cfg, list(res['points']), imgs, samples, continuous=True)
+    sum(out.values()).backward()
+    for k in ('loss_occ_0', 'loss_occ_1', 'loss_occ_2'):
+        assert rel(out[k], g['a_' + k]) <= 2e-5, (k, float(out[k]), float(g['a_' + k]))
+    for k in OCC_CONT_WATCH:      # parameters downstream of the 4-voxel BatchNorm layers (see the occupancy fixture)
+        want = torch.from_numpy(g[f'a_grad/{k}'])
+        got = sampled(sd[k].grad).reshape(want.shape)
+        if k.startswith('bbox_head'):
+            assert float((got - want).abs().max()) <= 2e-4 * float(want.abs().max()), k
+        else:
+            cos = float(torch.dot(got.flatten().double(), want.flatten().double()) / (got.norm() * want.norm()))
+            assert cos >= 0.999, (k, cos)

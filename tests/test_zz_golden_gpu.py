@@ -236,3 +236,23 @@ def test_continuous_detector_loss_and_gradients_match_reference():
         scale = float(want.abs().max())
         assert float((got - want).abs().max()) <= 2e-3 * scale, (ref_name, float((got - want).abs().max()), scale)
         assert rel(grad.double().norm(), g[f'a_gradnorm/{ref_name}']) <= 2e-3, ref_name
+
+
+def test_continuous_occupancy_loss_matches_reference():
+    from test_golden_cpu import continuous_occ_batch, continuous_occ_config
+    g = load('continuous_occ')
+    cfg = continuous_occ_config()
+    model, _ = product_state_dict(cfg, g, lambda s: s)
+    model = model.to(DEV).train()
+    data, _ = continuous_occ_batch()
+    data = model.data_preprocessor(data, True)
+    losses = model(**data, mode='loss')
+    sum(losses.values()).backward()
+    for k in ('loss_occ_0', 'loss_occ_1', 'loss_occ_2'):
+        assert rel(losses[k], g['a_' + k]) <= 1e-3, (k, float(losses[k]), float(g['a_' + k]))
+    params = dict(model.named_parameters())
+    for k in ('bbox_head.occ.0.weight', 'bbox_head.occ.2.weight'):
+        grad = params[k].grad.detach().cpu()
+        want = torch.from_numpy(g[f'a_grad/{k}'])
+        got = sampled(grad).reshape(want.shape)
+        assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max()), k
