@@ -196,3 +196,101 @@ class IndoorDetMetric:
         out = self.compute_metrics()
         self.results.clear()
         return out
+
+
+@METRICS.register_module()
+class GroundingMetric:
+    """``embodiedscan/eval/metrics/grounding_metric.py``: a prompt counts as found at threshold t when one of its 10
+    highest-scoring boxes overlaps a target box with 9-DoF IoU > t; accuracy overall and per Easy/Hard,
+    View-Dep/View-Indep, Unique/Multi split. The IoU of the 10 candidates runs in ``esb_box3d_overlap``.
+    Frozen: the top-10 come from a STABLE descending sort (torch's default argsort leaves ties unordered)."""
+
+    TYPES = ('Easy', 'Hard', 'View-Dep', 'View-Indep', 'Unique', 'Multi', 'Overall')
+
+    def __init__(self, iou_thr=(0.25, 0.5), collect_device='cpu', prefix=None, format_only=False, result_dir='', **kw):
+        self.iou_thr = [iou_thr] if isinstance(iou_thr, float) else list(iou_thr)
+        self.prefix, self.results = prefix, []
+
+    def process(self, data_batch, data_samples) -> None:
+        for ds in data_samples:
+            get = ds.get if hasattr(ds, 'get') else ds.__getitem__
+            pred = get('pred_instances_3d')
+            pred = dict(pred.items()) if hasattr(pred, 'items') else {k: getattr(pred, k) for k in pred.keys()}
+            self.results.append((get('eval_ann_info'), pred))
+
+    def ground_eval(self, gt_annos, det_annos, iou_fn: Optional[Callable] = None) -> Dict[str, float]:
+        assert len(det_annos) == len(gt_annos)
+        iou_fn = iou_fn or _device_iou
+        pred = {f'{o}@{t}': 0 for t in self.iou_thr for o in self.TYPES}
+        gt = {f'{o}@{t}': 1e-14 for t in self.iou_thr for o in self.TYPES}
+        for det, ann in zip(det_annos, gt_annos):
+            scores = torch.as_tensor(det['target_scores_3d']).reshape(-1)
+            top = torch.sort(scores, descending=True, stable=True).indices[:10].cpu()
+            iou = iou_fn(_as_boxes9(det['bboxes_3d'])[top], _gt_boxes9(ann['gt_bboxes_3d'])).float().cpu()
+            tags = ('View-Dep' if ann['is_view_dep'] else 'View-Indep', 'Hard' if ann['is_hard'] else 'Easy',
+                    'Unique' if ann['is_unique'] else 'Multi', 'Overall')
+            for t in self.iou_thr:
+                found = int(bool((iou > t).any()))
+                for tag in tags:
+                    gt[f'{tag}@{t}'] += 1
+                    pred[f'{tag}@{t}'] += found
+        return {k: pred[k] / max(gt[k], 1) for t in self.iou_thr for k in (f'{o}@{t}' for o in self.TYPES)}
+
+    def compute_metrics(self, results=None) -> Dict[str, float]:
+        results = self.results if results is None else results
+        anns, preds = zip(*results) if results else ((), ())
+        out = self.ground_eval(list(anns), list(preds))
+        return {'/'.join((self.prefix, k)): v for k, v in out.items()} if self.prefix else out
+
+    def evaluate(self, size=None):
+        out = self.compute_metrics()
+        self.results.clear()
+        return out
+
+
+@METRICS.register_module()
+class OccupancyMetric:
+    """``embodiedscan/eval/metrics/occupancy_metric.py``: per-class IoU of the arg-max occupancy (class 0 = geometry:
+    occupied vs empty), voxels with ground truth 255 (invisible) ignored. The per-scan counts are three ``bincount``s
+    on whatever device holds the prediction instead of ``num_class`` masked passes."""
+
+    def __init__(self, collect_device='cpu', prefix=None, batchwise_anns=False, **kw):
+        self.prefix, self.results, self.dataset_meta = prefix, [], {}
+
+    def process(self, data_batch, data_samples) -> None:
+        for ds in data_samples:
+            get = ds.get if hasattr(ds, 'get') else ds.__getitem__
+            pred = get('pred_occupancy')
+            gt4 = get('gt_occupancy').long().to(pred.device)
+            gt = torch.zeros_like(pred)
+            gt[gt4[:, 0], gt4[:, 1], gt4[:, 2]] = gt4[:, 3].to(pred.dtype)
+            if 'gt_occupancy_masks' in ds:
+                gt[~get('gt_occupancy_masks').to(pred.device)] = 255
+            self.results.append((gt, pred))
+
+    def compute_metrics(self, results=None) -> Dict[str, float]:
+        results = self.results if results is None else results
+        classes = self.dataset_meta['classes']
+        n = len(classes) + 1
+        score = torch.zeros((n, 3), dtype=torch.float64)
+        for gt, pred in results:
+            keep = gt != 255
+            g, p = gt[keep].long().clamp(max=n - 1), pred[keep].long().clamp(max=n - 1)
+            tp = torch.bincount(g[g == p], minlength=n)
+            cg, cp = torch.bincount(g, minlength=n), torch.bincount(p, minlength=n)
+            cnt = torch.stack([tp, cg, cp], 1).double().cpu()
+            cnt[0] = torch.tensor([float(((g != 0) & (p != 0)).sum()), float((g != 0).sum()), float((p != 0).sum())])
+            score += cnt
+        ret = {}
+        for i in range(n):
+            tp, a, b = score[i].tolist()
+            union = a + b - tp
+            if union == 0:                       # the reference skips classes whose IoU is 0/0
+                continue
+            ret['empty' if i == 0 else classes[i - 1]] = tp / union
+        return {'/'.join((self.prefix, k)): v for k, v in ret.items()} if self.prefix else ret
+
+    def evaluate(self, size=None):
+        out = self.compute_metrics()
+        self.results.clear()
+        return out

@@ -230,3 +230,43 @@ def continuous_occ_inputs(scan=8, n_views=3, per_view=1200):
     g = torch.Generator().manual_seed(300 + scan)
     ci['visible_occupancy_masks'] = [(torch.rand(*cfg['n_voxels'], generator=g) < 0.45).numpy() for _ in range(n_views)]
     return ci
+
+
+def grounding_metric_inputs():
+    """8 prompts: 40 candidate boxes each (a few jittered copies of the target at different quality + noise), scores."""
+    g = torch.Generator().manual_seed(51)
+    dets, anns = [], []
+    for i in range(8):
+        tgt = torch.cat([torch.rand(3, generator=g) * 4 - 2, 0.4 + torch.rand(3, generator=g),
+                         torch.rand(3, generator=g) - 0.5])[None]
+        boxes = torch.cat([torch.rand(40, 3, generator=g) * 4 - 2, 0.4 + torch.rand(40, 3, generator=g),
+                           torch.rand(40, 3, generator=g) - 0.5], 1)
+        scores = torch.rand(40, generator=g)
+        copies = {0: [], 1: [0.04], 2: [0.17], 3: [0.17, 0.04], 4: [0.3], 5: [0.04], 6: [0.17], 7: []}[i]
+        for j, mag in enumerate(copies):                                  # near-copies of the target, varying quality
+            b = tgt[0].clone()
+            b[:3] += mag * b[3:6] * torch.randn(3, generator=g)
+            b[3:6] *= 1 + mag * torch.randn(3, generator=g).clamp(-1, 1)
+            boxes[5 * j] = b
+            scores[5 * j] = 0.02 if i == 5 else 1.5 + j                   # prompt 5 buries its good box below the top 10
+        dets.append(dict(bboxes_3d=boxes, target_scores_3d=scores))
+        anns.append(dict(gt_bboxes_3d=tgt, is_view_dep=bool(i & 1), is_hard=bool(i & 2), is_unique=bool(i & 4)))
+    return dets, anns
+
+
+def occupancy_metric_inputs():
+    g = torch.Generator().manual_seed(52)
+    classes = [f'class{i}' for i in range(1, 9)]
+    samples = []
+    for i in range(3):
+        gt_grid = torch.randint(0, 9, (8, 8, 4), generator=g) * (torch.rand(8, 8, 4, generator=g) < 0.5)
+        gt_grid[gt_grid == 7] = 0                                            # class7 never in the ground truth
+        pred = torch.where(torch.rand(8, 8, 4, generator=g) < 0.6, gt_grid, torch.randint(0, 9, (8, 8, 4), generator=g))
+        pred[pred == 8] = 0                                                  # class8 never predicted
+        idx = torch.nonzero(gt_grid)
+        gt4 = torch.cat([idx, gt_grid[idx[:, 0], idx[:, 1], idx[:, 2]][:, None]], 1)
+        d = dict(pred_occupancy=pred, gt_occupancy=gt4)
+        if i:
+            d['gt_occupancy_masks'] = torch.rand(8, 8, 4, generator=g) < 0.7
+        samples.append(d)
+    return classes, samples

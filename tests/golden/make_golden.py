@@ -28,7 +28,7 @@ import refstubs  # noqa: E402
 
 refstubs.install()
 
-from cases import (HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs,  # noqa: E402
+from cases import (grounding_metric_inputs, occupancy_metric_inputs, HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs,  # noqa: E402
                    preprocess_inputs, target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_tensor  # noqa: E402
 
@@ -541,7 +541,42 @@ def gen_continuous_occ():
     save('continuous_occ', **out)
 
 
-GENERATORS = dict(continuous_occ=gen_continuous_occ, continuous=gen_continuous, augment=gen_augment, grounding=gen_grounding, detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions,
+def gen_metrics():
+    """f3: GroundingMetric.ground_eval (grounding_metric.py:78-150) and OccupancyMetric.process/compute_metrics
+    (occupancy_metric.py:44-110)."""
+    import json
+
+    import embodiedscan.eval.metrics.grounding_metric as gm
+    import embodiedscan.eval.metrics.occupancy_metric as om
+    from embodiedscan.structures import EulerDepthInstance3DBoxes
+
+    class _Table:
+        def __init__(self, data):
+            self.table = ''
+    for mod in (gm, om):
+        mod.AsciiTable = _Table
+        mod.MMLogger = type('L', (), dict(get_current_instance=staticmethod(lambda: None)))
+    dets, anns = grounding_metric_inputs()
+    box = lambda t: EulerDepthInstance3DBoxes(t.clone(), box_dim=9, origin=(.5, .5, .5))  # noqa: E731
+    metric = gm.GroundingMetric.__new__(gm.GroundingMetric)
+    metric.iou_thr = [0.25, 0.5]
+    ret = metric.ground_eval([dict(a, gt_bboxes_3d=box(a['gt_bboxes_3d'])) for a in anns],
+                             [dict(d, bboxes_3d=box(d['bboxes_3d'])) for d in dets])
+    print('grounding metric:', {k: round(v, 4) for k, v in ret.items()})
+    classes, samples = occupancy_metric_inputs()
+    occ = om.OccupancyMetric.__new__(om.OccupancyMetric)
+    occ.results, occ.dataset_meta = [], dict(classes=classes)
+    occ.process(None, [dict(d) for d in samples])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ret_occ = occ.compute_metrics(occ.results)
+    print('occupancy metric:', {k: round(float(v), 4) for k, v in ret_occ.items()})
+    save('metrics', grounding_json=np.array(json.dumps(ret, sort_keys=True)),
+         occupancy_json=np.array(json.dumps({k: float(v) for k, v in ret_occ.items()}, sort_keys=True)))
+
+
+GENERATORS = dict(metrics=gen_metrics, continuous_occ=gen_continuous_occ, continuous=gen_continuous, augment=gen_augment, grounding=gen_grounding, detector=gen_detector, occupancy=gen_occupancy, frontend=gen_frontend, functions=gen_functions,
                   eval=gen_eval)
 
 if __name__ == '__main__':

@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import (HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
+from cases import (grounding_metric_inputs, occupancy_metric_inputs, HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
                    target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_state_dict  # noqa: E402
 
@@ -515,3 +515,28 @@ def test_continuous_occupancy_loss_and_gradients_match_reference():
         else:
             cos = float(torch.dot(got.flatten().double(), want.flatten().double()) / (got.norm() * want.norm()))
             assert cos >= 0.999, (k, cos)
+
+
+def test_grounding_and_occupancy_metrics_match_reference():
+    """Host logic of GroundingMetric (IoU injected; the CUDA IoU is checked in -m gpu) and OccupancyMetric (pure torch
+    bincounts, same code on CPU and GPU tensors)."""
+    import json
+    from embodiedscan_b200.evaluation import GroundingMetric, OccupancyMetric
+    from oracle import eval_ref as E
+    g = load('metrics')
+    dets, anns = grounding_metric_inputs()
+    got = GroundingMetric(iou_thr=[0.25, 0.5]).ground_eval(
+        anns, dets, iou_fn=lambda p, q: torch.from_numpy(E.iou_matrix(p.numpy(), q.numpy())))
+    want = json.loads(str(g['grounding_json']))
+    assert set(got) == set(want) and 0.0 < want['Overall@0.5'] < want['Overall@0.25'] < 1.0
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])
+    classes, samples = occupancy_metric_inputs()
+    m = OccupancyMetric()
+    m.dataset_meta = dict(classes=classes)
+    m.process(None, samples)
+    got = m.evaluate()
+    want = json.loads(str(g['occupancy_json']))
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])

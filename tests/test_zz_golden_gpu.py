@@ -256,3 +256,23 @@ def test_continuous_occupancy_loss_matches_reference():
         want = torch.from_numpy(g[f'a_grad/{k}'])
         got = sampled(grad).reshape(want.shape)
         assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max()), k
+
+
+def test_grounding_and_occupancy_metrics_match_reference():
+    import json
+    from embodiedscan_b200.evaluation import GroundingMetric, OccupancyMetric
+    from test_golden_cpu import grounding_metric_inputs, occupancy_metric_inputs
+    g = load('metrics')
+    dets, anns = grounding_metric_inputs()
+    got = GroundingMetric(iou_thr=[0.25, 0.5]).ground_eval(anns, dets)          # IoU from esb_box3d_overlap
+    want = json.loads(str(g['grounding_json']))
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])
+    classes, samples = occupancy_metric_inputs()
+    m = OccupancyMetric()
+    m.dataset_meta = dict(classes=classes)
+    m.process(None, [{k: v.to(DEV) for k, v in s.items()} for s in samples])  # bincounts on the device
+    got = m.evaluate()
+    want = json.loads(str(g['occupancy_json']))
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])
