@@ -52,6 +52,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--torch-profile', default='', help='write a torch.profiler kernel table of 2 steps to this path')
+    ap.add_argument('--row-order', default=None, choices=['input', 'morton'],
+                    help='row order of the sparse tensors (default: ESB200_ROW_ORDER or input); morton = Z-ordered rows')
     return ap.parse_args()
 
 
@@ -199,6 +201,8 @@ def main():
     args = parse()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.row_order:
+        os.environ['ESB200_ROW_ORDER'] = args.row_order
 
     import torch.distributed as dist
     from embodiedscan_b200 import MODELS, _ffi
@@ -393,6 +397,7 @@ def main():
                                   f'{args.height}x{args.width} RGB-D, {args.points} points/scan, ResNet-50/16 + MinkResNet34 '
                                   f'+ FCAF3DHeadRotMat, AdamW + clip',
                       'global_batch': world * args.batch, 'parallelism': f'dp{world}',
+                      'row_order': os.environ.get('ESB200_ROW_ORDER', 'input'),
                       'l2': 'per-step working set (340 MB fp32 weights + multi-GB activations) exceeds the 126 MB L2; '
                             f'{n_distinct} distinct input batches alternate; {n_distinct} untimed setup steps precede the W warm-up steps',
                       'loss': {k: float(v) for k, v in logs.items()}},

@@ -13,6 +13,7 @@ Design: a *plan/execute* split. All integer work (dedup, strided maps, kernel ma
 coordinates, is built once per batch by ``CoordinateManager`` and cached, so every conv of a level shares one map.
 """
 import ctypes
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -410,6 +411,34 @@ def norm_apply_eval(x, mean, var, gamma, beta, eps, act=ACT_NONE, res=None):
 # =========================================================================================================
 # SparseTensor + modules (ME-named so reference-style model code reads the same)
 # =========================================================================================================
+def _spread3(v: torch.Tensor) -> torch.Tensor:
+    """Bits of a 16-bit value moved to every third position (int64), the classic Morton "part1by2"."""
+    v = v & 0xffff
+    v = (v | (v << 32)) & 0x1f00000000ffff
+    v = (v | (v << 16)) & 0x1f0000ff0000ff
+    v = (v | (v << 8)) & 0x100f00f00f00f00f
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3
+    v = (v | (v << 2)) & 0x1249249249249249
+    return v
+
+
+def morton_order(coords: torch.Tensor) -> torch.Tensor:
+    """Stable permutation that sorts raw voxel coordinates (N,4) [b,x,y,z] by (scan, Z-order curve of xyz).
+    Z-order is hierarchical: the first-occurrence parents of sorted rows (stride-2 maps), the children ``8*parent+k``
+    of generative maps and the appended rows of unions all inherit spatial locality from this one sort, so a 128-row
+    conv tile gathers from a compact neighbourhood. Stable => points of one voxel keep their input order, i.e. the
+    first-occurrence dedup picks the same point (and feature) as without the sort; only the ROW ORDER changes."""
+    c = coords.to(torch.int64)
+    key = (c[:, 0] << 48) | _spread3(c[:, 1] + 32768) | (_spread3(c[:, 2] + 32768) << 1) | (_spread3(c[:, 3] + 32768) << 2)
+    return torch.sort(key, stable=True).indices
+
+
+def row_order() -> str:
+    """'input' (default: rows in first-occurrence order of the input points, the order the parity tests pin) or
+    'morton' (opt-in through ESB200_ROW_ORDER=morton; same voxels, same features, Z-ordered rows)."""
+    return os.environ.get('ESB200_ROW_ORDER', 'input')
+
+
 class SparseTensor:
 
     def __init__(self, features: torch.Tensor, coordinates: Optional[torch.Tensor] = None, coordinate_map_key=None,
@@ -419,6 +448,9 @@ class SparseTensor:
             if coordinate_manager is None:
                 coordinate_manager = CoordinateManager(features.device)
             coords = coordinates.to(device=features.device, dtype=torch.int32)
+            if row_order() == 'morton' and coords.shape[0]:
+                order = morton_order(coords)
+                coords, features = coords[order].contiguous(), features[order]
             key, in2out = coordinate_manager.insert(coords, 1, batch_size)
             n = coordinate_manager.maps[key].n
             # first occurrence wins: scatter in reverse order so the lowest row index is written last

@@ -125,3 +125,37 @@ def test_continuous_detector_view_prefix_painting_control_flow(monkeypatch):
     assert f.shape == (coords.shape[0], 5 + 7) and torch.equal(f[:, :5], feats3d)
     want = torch.tensor([1., 0., 3.])[coords[:, 0].long()]
     assert torch.equal(f[:, 5:], want[:, None].expand(-1, 7))
+
+
+def test_morton_row_order_is_stable_and_hierarchical():
+    """ESB200_ROW_ORDER=morton (opt-in): one stable sort of the raw voxel coordinates by (scan, Z-order)."""
+    from embodiedscan_b200.sparse import _spread3, morton_order
+    from oracle import sparse_ref as S
+    g = torch.Generator().manual_seed(1)
+    v = torch.randint(0, 65536, (200, ), generator=g)
+    slow = torch.tensor([sum(((int(x) >> i) & 1) << (3 * i) for i in range(16)) for x in v])
+    assert torch.equal(_spread3(v), slow)
+    coords = torch.cat([torch.randint(0, 2, (4000, 1), generator=g), torch.randint(-40, 40, (4000, 3), generator=g)], 1).int()
+    order = morton_order(coords)
+    assert torch.equal(torch.sort(order).values, torch.arange(4000)), 'a permutation'
+    sc = coords[order]
+    # stable: rows of one voxel keep their input order, so first-occurrence dedup keeps the same point per voxel
+    u0, in2out0 = S.unique_first(coords.numpy())
+    u1, in2out1 = S.unique_first(sc.numpy())
+    first0 = np.full(len(u0), 10 ** 9)
+    np.minimum.at(first0, in2out0, np.arange(4000))
+    first1 = np.full(len(u1), 10 ** 9)
+    np.minimum.at(first1, in2out1, order.numpy())            # original index of the first sorted row of each voxel
+    k0 = {tuple(c): f for c, f in zip(u0.tolist(), first0.tolist())}
+    k1 = {tuple(c): f for c, f in zip(u1.tolist(), first1.tolist())}
+    assert k0 == k1, 'same voxels, same representative point'
+    # hierarchical: scans stay contiguous, and the first-occurrence parents at stride 2, 4, 8 are Z-ordered themselves
+
+    def zkey(c):
+        c = torch.as_tensor(c).long()
+        return (c[:, 0] << 48) | _spread3(c[:, 1] + 32768) | (_spread3(c[:, 2] + 32768) << 1) | (_spread3(c[:, 3] + 32768) << 2)
+    cur = u1
+    for stride in (2, 4, 8):
+        cur = S.unique_first(cur, stride)[0]
+        k = zkey(cur)
+        assert bool((k[1:] > k[:-1]).all()), f'stride-{stride} parents inherit the order'
