@@ -276,3 +276,17 @@ def test_grounding_and_occupancy_metrics_match_reference():
     want = json.loads(str(g['occupancy_json']))
     for k in want:
         assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])
+
+
+def test_detector_loss_is_invariant_to_the_row_order(monkeypatch):
+    """ESB200_ROW_ORDER=morton: same voxels and features in Z-ordered rows -> the same losses (order-invariant sums)."""
+    monkeypatch.setenv('ESB200_ROW_ORDER', 'morton')
+    g = load('detector_g1')
+    cfg = det_config()
+    model, _ = product_state_dict(cfg, g, adjust_fcaf3d_head)
+    model = model.to(DEV).train()
+    batch = det_inputs(2, True)
+    data = model.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
+    losses = model(**data, mode='loss')
+    for k in ('loss_center', 'loss_bbox', 'loss_cls'):
+        assert rel(losses[k], g[f'b_{k}']) <= 1e-3, (k, float(losses[k]), float(g[f'b_{k}']))
