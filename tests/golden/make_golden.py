@@ -113,6 +113,12 @@ def build_reference_detector(cfg):
     return MODELS.build(c)
 
 
+# 650: the cut of every pruned level falls between distinct scores. Children whose parents were pruned away interpolate to
+# exactly 0.0, a plateau of hundreds of tied voxels; a cut inside it (400, 500, 800 ...) leaves the survivors to
+# torch.topk's unspecified tie order, i.e. the reference itself is implementation-defined there (frozen rule: lowest row)
+DET_PRUNE = int(os.environ.get('DET_PRUNE', 650))
+
+
 def gen_detector():
     from oracle import model_ref as M
     cfg = det_config()
@@ -144,6 +150,20 @@ def gen_detector():
             out[f'{tag}_grad/{k}'] = g if g.numel() <= 4096 else g.flatten()[:: max(g.numel() // 4096, 1)][:4096]
             out[f'{tag}_gradnorm/{k}'] = g.double().norm()
         out[f'{tag}_n_points'] = np.array([len(p) for p in batch['inputs']['points']])
+    # active pruning (fcaf3d_head.py:1091-1114): keep the top-PRUNE voxels per scan by interpolated parent score
+    batch = det_inputs(1, False)
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    model.train()
+    model.bbox_head.pts_prune_threshold = DET_PRUNE
+    for p in model.parameters():
+        p.grad = None
+    losses = model(dict(points=batch['inputs']['points'], imgs=imgs), ref_data_samples(batch['data_samples']), mode='loss')
+    for k, v in losses.items():
+        out[f'c_{k}'] = v
+    out['c_prune'] = np.int64(DET_PRUNE)
+    print('pruned case losses', {k: round(float(v.detach()), 5) for k, v in losses.items()})
+    model.bbox_head.pts_prune_threshold = cfg['bbox_head']['pts_prune_threshold']
     # predict: three classes clear the score threshold, top-50 per level exercises the top-k path
     batch = det_inputs(1, False)
     imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],

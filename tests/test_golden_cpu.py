@@ -83,6 +83,22 @@ def test_detector_loss_and_gradients_match_reference(tag, n_scans, augment):
         assert rel(grad.double().norm(), g[f'{tag}_gradnorm/{ref_name}']) <= 5e-4, ref_name   # rotation columns: atan2/asin chains
 
 
+def test_detector_loss_with_active_pruning_matches_reference():
+    from oracle import model_ref as M
+    g = load('detector_g1')
+    cfg = det_config()
+    cfg['bbox_head']['pts_prune_threshold'] = int(g['c_prune'])
+    _, sd = product_state_dict(cfg, g, adjust_fcaf3d_head)
+    batch = det_inputs(1, False)
+    imgs = M.preprocess_imgs(torch.stack(batch['inputs']['img']), cfg['data_preprocessor']['mean'],
+                             cfg['data_preprocessor']['std'])
+    with torch.no_grad():
+        out = M.detector_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
+    assert rel(g['c_loss_cls'], g['a_loss_cls']) > 1e-3, 'pruning must change the result'
+    for k in ('loss_center', 'loss_bbox', 'loss_cls'):
+        assert rel(out[k], g[f'c_{k}']) <= 2e-5, (k, float(out[k]), float(g[f'c_{k}']))
+
+
 def test_detector_predictions_match_reference():
     from oracle import model_ref as M
     g = load('detector_g1')

@@ -290,3 +290,17 @@ def test_detector_loss_is_invariant_to_the_row_order(monkeypatch):
     losses = model(**data, mode='loss')
     for k in ('loss_center', 'loss_bbox', 'loss_cls'):
         assert rel(losses[k], g[f'b_{k}']) <= 1e-3, (k, float(losses[k]), float(g[f'b_{k}']))
+
+
+def test_detector_loss_with_active_pruning_matches_reference():
+    g = load('detector_g1')
+    cfg = det_config()
+    cfg['bbox_head']['pts_prune_threshold'] = int(g['c_prune'])
+    model, _ = product_state_dict(cfg, g, adjust_fcaf3d_head)
+    model = model.to(DEV).train()
+    batch = det_inputs(1, False)
+    data = model.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
+    with torch.no_grad():
+        losses = model(**data, mode='loss')
+    for k in ('loss_center', 'loss_bbox', 'loss_cls'):
+        assert rel(losses[k], g[f'c_{k}']) <= 1e-3, (k, float(losses[k]), float(g[f'c_{k}']))
