@@ -270,3 +270,8 @@ def occupancy_metric_inputs():
             d['gt_occupancy_masks'] = torch.rand(8, 8, 4, generator=g) < 0.7
         samples.append(d)
     return classes, samples
+
+
+def box_coder_inputs():
+    g = torch.Generator().manual_seed(61)
+    return torch.rand(2, 7, 3, generator=g) * 4 - 2, 0.7 * torch.randn(2, 7, 12, generator=g)

@@ -28,7 +28,7 @@ import refstubs  # noqa: E402
 
 refstubs.install()
 
-from cases import (grounding_metric_inputs, occupancy_metric_inputs, HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs,  # noqa: E402
+from cases import (box_coder_inputs, grounding_metric_inputs, occupancy_metric_inputs, HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs,  # noqa: E402
                    preprocess_inputs, target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_tensor  # noqa: E402
 
@@ -313,6 +313,14 @@ def gen_functions():
     # a12: euler_box3d.py:137-184 corner order and rotation
     boxes = target_cases()['regular'][1]
     out['corners'] = EulerDepthInstance3DBoxes(boxes.clone(), box_dim=9, origin=(.5, .5, .5)).corners
+    # a15: GroundingHead._bbox_pred_to_bbox (grounding_head.py:267-363), both coders, 9- and 12-channel regression
+    from embodiedscan.models.dense_heads.grounding_head import GroundingHead
+    pts, reg = box_coder_inputs()
+    for coder in ('baseline', 'FCAF'):
+        gh = GroundingHead.__new__(GroundingHead)
+        gh.box_coder = coder
+        for nreg in (9, 12):
+            out[f'coder_{coder}_{nreg}'] = gh._bbox_pred_to_bbox(pts.clone(), reg[..., :nreg].clone())
     save('functions', **out)
 
 

@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 if GOLD not in sys.path:
     sys.path.insert(0, GOLD)
 
-from cases import (grounding_metric_inputs, occupancy_metric_inputs, HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
+from cases import (box_coder_inputs, grounding_metric_inputs, occupancy_metric_inputs, HashTextEncoder, augment_inputs, continuous_inputs, continuous_occ_inputs, det_config, det_inputs, eval_inputs, fusion_inputs, ground_config, ground_inputs, occ_config, occ_inputs, preprocess_inputs,  # noqa: E402
                    target_cases, unproject_inputs)
 from weights import adjust_fcaf3d_head, adjust_for_predict, adjust_grounder, fill_state_dict  # noqa: E402
 
@@ -556,3 +556,20 @@ def test_grounding_and_occupancy_metrics_match_reference():
     assert set(got) == set(want)
     for k in want:
         assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])
+
+
+@pytest.mark.parametrize('coder', ['baseline', 'FCAF'])
+@pytest.mark.parametrize('nreg', [9, 12])
+def test_grounding_box_coders_match_reference(coder, nreg):
+    """GroundingHead._bbox_pred_to_bbox of the product (torch ops, device-agnostic) against the reference's."""
+    from embodiedscan_b200.grounding import GroundingHead
+    g = load('functions')
+    pts, reg = box_coder_inputs()
+    gh = GroundingHead.__new__(GroundingHead)
+    gh.box_coder = coder
+    got = gh._bbox_pred_to_bbox(pts.clone(), reg[..., :nreg].clone())
+    want = torch.from_numpy(g[f'coder_{coder}_{nreg}'])
+    assert got.shape == want.shape
+    assert float((got[..., :6] - want[..., :6]).abs().max()) <= 1e-5
+    dang = torch.remainder(got[..., 6:] - want[..., 6:] + np.pi, 2 * np.pi) - np.pi
+    assert float(dang.abs().max()) <= 1e-5
