@@ -1,5 +1,6 @@
-"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py) — PARITY UNPINNED: the reference ships no tests or golden vectors
-for this path and its dependencies (MinkowskiEngine, mmcv, mmdet, pytorch3d) are not installable here.
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py). Pinned by tests/golden/grounding_g4.npz (the reference's own
+grounder, neck, decoder, head, assigner and match costs executed by tests/golden/make_golden.py); the mmcv / mmdet /
+pytorch3d / MinkowskiEngine arithmetic underneath stays unpinned (not installable here).
 
 CPU restatement of the grounding path, evaluated functionally from the product's state_dict:
   embodiedscan/models/necks/mink_neck.py:133-244                         (pruned sparse FPN, coarse -> fine concat)

@@ -1,5 +1,6 @@
-"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py) — PARITY UNPINNED: the reference ships no tests or golden vectors
-for this path and its dependencies (MinkowskiEngine, mmcv, mmdet) are not installable here.
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py). Pinned by tests/golden/occupancy_g3.npz and continuous_occ.npz
+(the reference's own DenseFusionOccPredictor / EmbodiedOccPredictor, neck, head and losses executed by
+tests/golden/make_golden.py); the MinkowskiEngine / mmdet arithmetic underneath stays unpinned (not installable here).
 
 CPU restatement of the occupancy path, evaluated functionally from the product's state_dict:
   embodiedscan/models/detectors/dense_fusion_occ.py:101-265 (extract_feat), :267-295 (loss)

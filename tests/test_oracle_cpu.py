@@ -1,5 +1,6 @@
-"""CPU: pin the oracle with closed forms and the reference's only known-answer vector (parity is otherwise unpinned:
-the reference ships no tests or fixtures — oracle/__init__.py)."""
+"""CPU: pin the oracle's THIRD-PARTY semantics with closed forms and the reference's only known-answer vector (the
+reference's own code is pinned by the goldens of tests/test_golden_cpu.py; what lives inside MinkowskiEngine / mmcv /
+pytorch3d cannot be executed here — oracle/__init__.py)."""
 import math
 
 import numpy as np
