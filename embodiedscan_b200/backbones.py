@@ -121,6 +121,46 @@ class _BiasResAct(torch.autograd.Function):
         return g, None, (g if ctx.has_res else None), None
 
 
+def conv2d_tc(x: torch.Tensor, w_ohwi: torch.Tensor, bias, res, relu: bool, kh: int, kw: int, stride: int, pad: int):
+    """EXPERIMENTAL (ESB200_CONV2D=tc): the folded conv + bias + residual + ReLU block in ONE tcgen05 implicit-GEMM
+    launch (csrc/conv2d_tc.cu). x (N,Cin,H,W) bf16 in channels_last memory; w_ohwi (Cout, r_pad) bf16 from
+    :func:`pack_ohwi`; bias (Cout,) fp32 or None; res like the output or None. Forward only (frozen / inference)."""
+    from . import _ffi
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    N, cin, H, W = x.shape
+    cout, r_pad = w_ohwi.shape
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    y = torch.empty((N, cout, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    if res is not None:
+        assert res.shape == y.shape and res.dtype == torch.bfloat16
+        if not res.is_contiguous(memory_format=torch.channels_last):
+            res = res.contiguous(memory_format=torch.channels_last)
+    if bias is not None:
+        bias = bias.float().contiguous()
+    _ffi.call('esb_conv2d_tc_fwd', x.data_ptr(), w_ohwi.data_ptr(), _ffi.ptr(bias), _ffi.ptr(res), y.data_ptr(), N, H, W,
+              cin, cout, kh, kw, stride, pad, r_pad, 1 if relu else 0, _ffi.stream())
+    return y
+
+
+def pack_ohwi(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, kh, kw) -> (Cout, r_pad) bf16: filter taps in (ky, kx, ci) order, rows zero padded to a multiple of
+    64 reduction elements — the K-major B operand of csrc/conv2d_tc.cu."""
+    cout = w.shape[0]
+    flat = w.detach().permute(0, 2, 3, 1).reshape(cout, -1)
+    r = flat.shape[1]
+    r_pad = (r + 63) // 64 * 64
+    out = torch.zeros((cout, r_pad), dtype=torch.bfloat16, device=w.device)
+    out[:, :r] = flat.to(torch.bfloat16)
+    return out
+
+
+def conv2d_backend() -> str:
+    """'cudnn' (default, the measured path) or 'tc' (ESB200_CONV2D=tc: own tcgen05 kernel for blocks that need no
+    gradient — the frozen stem-side stages in training, every block in inference)."""
+    import os
+    return os.environ.get('ESB200_CONV2D', 'cudnn')
+
+
 class _ConvBN(nn.Module):
     """Conv2d(bias=False) followed by a BatchNorm2d; evaluated folded when the norm is in eval mode."""
 
@@ -166,6 +206,17 @@ class _ConvBN(nn.Module):
             w = self._const_w.get(x.dtype)
             if w is None:
                 w = self._const_w[x.dtype] = (conv.weight.detach() * scale4).to(x.dtype)
+        if (conv2d_backend() == 'tc' and x.is_cuda and x.dtype == torch.bfloat16 and w.shape[1] % 8 == 0
+                and w.shape[0] % 8 == 0 and x.is_contiguous(memory_format=torch.channels_last)
+                and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+                and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad
+                                                      or (res is not None and res.requires_grad)))):
+            wp = self._const_w.get('ohwi') if not conv.weight.requires_grad else None
+            if wp is None:
+                wp = pack_ohwi(w)
+                if not conv.weight.requires_grad:
+                    self._const_w['ohwi'] = wp
+            return conv2d_tc(x, wp, b, res, relu, w.shape[2], w.shape[3], conv.stride[0], conv.padding[0])
         y = F.conv2d(x, w, None, conv.stride, conv.padding)
         if y.is_cuda and y.shape[1] % 8 == 0 and y.is_contiguous(memory_format=torch.channels_last):
             return _BiasResAct.apply(y, b, res, SP.ACT_RELU if relu else SP.ACT_NONE)   # bias + residual + ReLU fused

@@ -1,0 +1,236 @@
+// esb200 — dense 2D convolution on the 5th-generation tensor cores (tcgen05 + TMEM), bf16 in / fp32 accumulate:
+// the per-view image backbone (mmdet.ResNet(depth=50, base_channels=16) called at
+// embodiedscan/models/detectors/sparse_featfusion_single_stage.py:130-136) as an implicit GEMM with the frozen
+// BatchNorm folded into the weights and bias + residual + ReLU fused into the epilogue.
+//
+// STATUS: EXPERIMENTAL. Written after round 1's GPU budget was spent: it compiles for sm_100a and is reachable only
+// through ESB200_CONV2D=tc (backbones.py) and its own parity test; the measured path still calls cuDNN.
+//
+// GEMM view: M = n_img*Ho*Wo output pixels, N = Cout, reduction R = kh*kw*Cin ordered (ky, kx, ci) — i.e. the weight
+// in OHWI (= PyTorch channels_last) layout IS the K-major B operand, row n = output channel, R contiguous, zero padded
+// to R_pad (multiple of 64) by the host. A is never materialised (no im2col buffer): a CTA owns 128 output pixels x
+// N_TILE channels and gathers, per 64-wide reduction chunk, eight 16-byte pieces per pixel straight from the NHWC
+// activations with cp.async (zero-fill outside the image / beyond R), into the 128B-swizzled K-major layout the
+// sparse kernel uses. Thin layers (Cin = 16, 32) pack 4 or 2 filter taps into one 64-wide chunk, so a 3x3x16 filter
+// is 3 chunks instead of 9. Same warp roles as spconv_tc.cu: warps 0-3 gather then run the epilogue (TMEM lane =
+// pixel), warp 4 allocates TMEM and issues tcgen05.mma; full/empty mbarrier ring, tcgen05.commit frees stages.
+//
+// Roofline: HBM. Algorithmic bytes per image = (H*W*Cin + Ho*Wo*Cout [+ residual]) * 2 + R_pad*Cout*2.
+#include "tc_common.cuh"
+
+using namespace esb_tc;
+
+namespace {
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(160)
+conv2d_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wt,
+                     const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res,
+                     __nv_bfloat16* __restrict__ y, long long M, int H, int W, int cin, int Ho, int Wo, int cout, int kh,
+                     int kw, int stride, int pad, int r_pad, int relu) {
+  constexpr int B_STAGE_BYTES = N_TILE * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int LAG = STAGES - 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const long long tile = blockIdx.x;
+  const int n0 = blockIdx.y * N_TILE;
+  const int total = r_pad / TC_BK;                 // >= 1
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, N_TILE);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- producers: 8 lanes fetch the 8 x 16 B pieces of one pixel's chunk (see spconv_tc.cu) ----------
+    const int t = threadIdx.x;
+    const int sub = t & 7, rgrp = t >> 3;
+    const uint32_t sw = (uint32_t)(rgrp & 7);
+    const uint32_t a_thread_off = (uint32_t)((rgrp >> 3) * 1024 + (rgrp & 7) * 128) + ((sub ^ sw) << 4);
+    const int taps = kh * kw;
+    int iy0[8], ix0[8];
+    long long img_off[8];                          // element offset of the pixel's image in x, or -1 beyond M
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long m = tile * TC_M + rgrp + 16 * i;
+      if (m < M) {
+        const long long n = m / ((long long)Ho * Wo);
+        const int rem = (int)(m - n * (long long)Ho * Wo);
+        const int oy = rem / Wo, ox = rem - oy * Wo;
+        iy0[i] = oy * stride - pad;
+        ix0[i] = ox * stride - pad;
+        img_off[i] = n * (long long)H * W * cin;
+      } else {
+        iy0[i] = ix0[i] = 0;
+        img_off[i] = -1;
+      }
+    }
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+      // this thread's 8 reduction elements of the chunk all belong to one filter tap (cin % 8 == 0)
+      const int r0 = it * TC_BK + sub * 8;
+      const int tap = r0 / cin, ch = r0 - tap * cin;
+      const int ky = tap / kw, kx = tap - ky * kw;
+      const bool tap_ok = tap < taps;
+      const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES) + a_thread_off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int iy = iy0[i] + ky, ix = ix0[i] + kx;
+        const bool ok = tap_ok && img_off[i] >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const __nv_bfloat16* src = ok ? x + img_off[i] + ((long long)iy * W + ix) * cin + ch : x;
+        cp_async16_ca(a_base + i * 2048, src, ok ? 16 : 0);
+      }
+      const uint32_t b_base = smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES);
+#pragma unroll
+      for (int q = 0; q < N_TILE / 16; ++q) {
+        const int idx = q * 128 + t;
+        const int n = idx >> 3, j = idx & 7;
+        const bool ok = n0 + n < cout;
+        cp_async16_cg(b_base + (n >> 3) * 1024 + (n & 7) * 128 + ((j ^ (n & 7)) << 4),
+                      ok ? wt + (long long)(n0 + n) * r_pad + it * TC_BK + j * 8 : wt, ok ? 16 : 0);
+      }
+      cp_async_commit();
+      if (it >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(&full_bar[(it - LAG) % STAGES]);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int d = (total > LAG ? total - LAG : 0); d < total; ++d) mbar_arrive(&full_bar[d % STAGES]);
+
+    // ---------------- epilogue: + bias, + residual, ReLU, bf16 ----------------
+    const long long row = tile * TC_M + threadIdx.x;        // TMEM lane = pixel of the tile
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (row < M) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = n0 + c0 + 8 * q;
+          if (c < cout) {                                   // cout % 8 == 0: a group of 8 is all in or all out
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * q + e]);
+            if (bias != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (res != nullptr) {
+              const uint4 r = *reinterpret_cast<const uint4*>(res + row * cout + c);
+              const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 rf = __bfloat1622float2(rp[e]);
+                f[2 * e] += rf.x;
+                f[2 * e + 1] += rf.y;
+              }
+            }
+            if (relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16(__float_as_uint(f[0]), __float_as_uint(f[1]));
+            o.y = pack_bf16(__float_as_uint(f[2]), __float_as_uint(f[3]));
+            o.z = pack_bf16(__float_as_uint(f[4]), __float_as_uint(f[5]));
+            o.w = pack_bf16(__float_as_uint(f[6]), __float_as_uint(f[7]));
+            *reinterpret_cast<uint4*>(y + row * cout + c) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---------------- MMA issuer (warp 4) ----------------
+    const uint32_t idesc = make_idesc(TC_M, N_TILE, 0, 0);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&full_bar[s], (it / STAGES) & 1);
+      tc_fence_after();
+      if ((threadIdx.x & 31) == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 16; ++kk)
+          umma_bf16(tmem_base, make_desc(a_addr + kk * 32, 16, 1024), make_desc(b_addr + kk * 32, 16, 1024), idesc,
+                    (it > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (it == total - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, N_TILE);
+  }
+}
+
+template <int N_TILE, int STAGES>
+int launch_conv2d(const void* x, const void* wt, const float* bias, const void* res, void* y, long long M, int H, int W,
+                  int cin, int Ho, int Wo, int cout, int kh, int kw, int stride, int pad, int r_pad, int relu,
+                  cudaStream_t stream) {
+  size_t smem = (size_t)STAGES * (A_STAGE_BYTES + N_TILE * 128) + 1024 + 256;
+  auto kern = conv2d_tc_fwd_kernel<N_TILE, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { esb_set_error("conv2d_tc_fwd: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
+  dim3 grid(esb_div_up(M, TC_M), esb_div_up(cout, N_TILE));
+  kern<<<grid, 160, smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)wt, bias, (const __nv_bfloat16*)res,
+                                    (__nv_bfloat16*)y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu);
+  return ESB_OK;
+}
+
+}  // namespace
+
+extern "C" int esb_conv2d_tc_fwd(const void* x, const void* w_ohwi, const float* bias, const void* residual, void* y,
+                                 int n_img, int H, int W, int cin, int cout, int kh, int kw, int stride, int pad,
+                                 int r_pad, int relu, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESB_CHECK_ARG(cin > 0 && cin % 8 == 0, "esb_conv2d_tc_fwd: Cin must be a positive multiple of 8 (16-byte pieces)");
+  ESB_CHECK_ARG(cout > 0 && cout % 8 == 0, "esb_conv2d_tc_fwd: Cout must be a positive multiple of 8");
+  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && stride >= 1 && pad >= 0, "esb_conv2d_tc_fwd: bad filter geometry");
+  ESB_CHECK_ARG(r_pad % 64 == 0 && r_pad >= kh * kw * cin, "esb_conv2d_tc_fwd: r_pad must be kh*kw*Cin rounded up to 64");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tc_fwd: empty output");
+  const long long M = (long long)n_img * Ho * Wo;
+  if (M == 0) return ESB_OK;
+  const long long row_tiles = (M + TC_M - 1) / TC_M;
+  int rc;
+  if (cout > 128 && row_tiles * ((cout + 255) / 256) >= 148)
+    rc = launch_conv2d<256, 4>(x, w_ohwi, bias, residual, y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, stream);
+  else if (cout > 64)
+    rc = launch_conv2d<128, 3>(x, w_ohwi, bias, residual, y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, stream);
+  else if (cout > 32)
+    rc = launch_conv2d<64, 4>(x, w_ohwi, bias, residual, y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, stream);
+  else
+    rc = launch_conv2d<32, 4>(x, w_ohwi, bias, residual, y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, stream);
+  if (rc != ESB_OK) return rc;
+  ESB_CUDA_LAUNCH_CHECK("conv2d_tc_fwd_kernel");
+  return ESB_OK;
+}

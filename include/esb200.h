@@ -85,6 +85,14 @@ int esb_act_fwd(const void* x, void* y, long long n, int act, int dtype, void* s
 int esb_bias_act_fwd(const void* x, const float* bias, const void* res, void* y, long long rows, int C, int act,
                      int dtype, void* stream);
 int esb_act_bwd(const void* dy, const void* y, void* dx, long long n, int act, int dtype, void* stream);
+/* EXPERIMENTAL (compiled, not on the measured path yet): the folded conv+BN(+residual)(+ReLU) block of the per-view 2D
+ * ResNet (mmdet.ResNet called at embodiedscan/models/detectors/sparse_featfusion_single_stage.py:130-136) as ONE
+ * tcgen05 implicit GEMM. x (n_img,H,W,cin) bf16 NHWC; w_ohwi (cout, r_pad) bf16 = the filter in (ky,kx,ci) order,
+ * each row zero padded from kh*kw*cin to r_pad (multiple of 64); bias (cout) fp32 or NULL; residual / y
+ * (n_img,Ho,Wo,cout) bf16 NHWC, residual may be NULL. cin % 8 == 0, cout % 8 == 0. */
+int esb_conv2d_tc_fwd(const void* x, const void* w_ohwi, const float* bias, const void* residual, void* y, int n_img,
+                      int H, int W, int cin, int cout, int kh, int kw, int stride, int pad, int r_pad, int relu,
+                      void* stream);
 
 /* ---- point painting (batch_point_sample + apply_3d_transformation + batch_points_cam2img + F.grid_sample;
  * embodiedscan/models/layers/fusion_layers/point_fusion.py:208-311, structures/bbox_3d/utils.py:289-332) -------- */

@@ -304,3 +304,27 @@ def test_detector_loss_with_active_pruning_matches_reference():
         losses = model(**data, mode='loss')
     for k in ('loss_center', 'loss_bbox', 'loss_cls'):
         assert rel(losses[k], g[f'c_{k}']) <= 1e-3, (k, float(losses[k]), float(g[f'c_{k}']))
+
+
+# ------------------------------------------------------------------------------------------------ experimental kernels
+@pytest.mark.xfail(strict=False, reason='conv2d_tc.cu was written without GPU access (round 1 budget spent); it is not on '
+                   'the measured path (ESB200_CONV2D=tc opts in) and gets its first run here')
+def test_conv2d_tc_forward_matches_torch():
+    """Runs in a CHILD process with a hard timeout: a first-run tcgen05 kernel that deadlocks or faults must not take
+    the test session (or the CUDA context of the other tests) with it."""
+    import json
+    import os
+    import subprocess
+    import sys
+    child = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'conv2d_tc_child.py')
+    proc = subprocess.Popen([sys.executable, child], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        out, err = proc.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        proc.kill()                      # exactly the PID started above
+        proc.communicate()
+        pytest.fail('conv2d_tc child timed out (kernel hang?)')
+    lines = [json.loads(l) for l in out.splitlines() if l.startswith('{')]
+    assert proc.returncode == 0 and len(lines) == 7, (proc.returncode, out[-2000:], err[-2000:])
+    bad = [l for l in lines if not l['ok']]
+    assert not bad, bad
