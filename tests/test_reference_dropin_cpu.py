@@ -23,6 +23,8 @@ def load_config(path):
     ('configs/detection/cont-det3d_8xb1_embodiedscan-3d-284class-9dof.py', 'Embodied3DDetector'),
     ('configs/occupancy/mv-occ_8xb1_embodiedscan-occ-80class.py', 'DenseFusionOccPredictor'),
     ('configs/occupancy/cont-occ_8xb1_embodiedscan-occ-80class.py', 'EmbodiedOccPredictor'),
+    ('configs/grounding/mv-grounding_8xb12_embodiedscan-vg-9dof.py', 'SparseFeatureFusion3DGrounder'),
+    ('configs/grounding/mv-grounding_8xb12_embodiedscan-vg-9dof_fcaf-coder.py', 'SparseFeatureFusion3DGrounder'),
 ])
 def test_reference_registry_builds_esb200_from_unmodified_configs(cfg_file, cls_name):
     if GOLD not in sys.path:
