@@ -215,6 +215,43 @@ def test_grounder_predictions_match_reference():
 
 
 # ------------------------------------------------------------------------------------------------ continuous (f4)
+def test_grounding_and_occupancy_metrics_match_reference():
+    import json
+    from embodiedscan_b200.evaluation import GroundingMetric, OccupancyMetric
+    from test_golden_cpu import grounding_metric_inputs, occupancy_metric_inputs
+    g = load('metrics')
+    dets, anns = grounding_metric_inputs()
+    got = GroundingMetric(iou_thr=[0.25, 0.5]).ground_eval(anns, dets)          # IoU from esb_box3d_overlap
+    want = json.loads(str(g['grounding_json']))
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])
+    classes, samples = occupancy_metric_inputs()
+    m = OccupancyMetric()
+    m.dataset_meta = dict(classes=classes)
+    m.process(None, [{k: v.to(DEV) for k, v in s.items()} for s in samples])  # bincounts on the device
+    got = m.evaluate()
+    want = json.loads(str(g['occupancy_json']))
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])
+
+
+def test_detector_loss_with_active_pruning_matches_reference():
+    g = load('detector_g1')
+    cfg = det_config()
+    cfg['bbox_head']['pts_prune_threshold'] = int(g['c_prune'])
+    model, _ = product_state_dict(cfg, g, adjust_fcaf3d_head)
+    model = model.to(DEV).train()
+    batch = det_inputs(1, False)
+    data = model.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
+    with torch.no_grad():
+        losses = model(**data, mode='loss')
+    for k in ('loss_center', 'loss_bbox', 'loss_cls'):
+        assert rel(losses[k], g[f'c_{k}']) <= 1e-3, (k, float(losses[k]), float(g[f'c_{k}']))
+
+
+# ------------------------------------------------------------------------------------------------ experimental kernels
+
+# ---- least-proven paths last: a fault here cannot poison the CUDA context of the tests above ----
 def test_continuous_detector_loss_and_gradients_match_reference():
     from test_golden_cpu import CONT_WATCH, continuous_batch, continuous_config
     g = load('continuous_det')
@@ -258,26 +295,6 @@ def test_continuous_occupancy_loss_matches_reference():
         assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max()), k
 
 
-def test_grounding_and_occupancy_metrics_match_reference():
-    import json
-    from embodiedscan_b200.evaluation import GroundingMetric, OccupancyMetric
-    from test_golden_cpu import grounding_metric_inputs, occupancy_metric_inputs
-    g = load('metrics')
-    dets, anns = grounding_metric_inputs()
-    got = GroundingMetric(iou_thr=[0.25, 0.5]).ground_eval(anns, dets)          # IoU from esb_box3d_overlap
-    want = json.loads(str(g['grounding_json']))
-    for k in want:
-        assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])
-    classes, samples = occupancy_metric_inputs()
-    m = OccupancyMetric()
-    m.dataset_meta = dict(classes=classes)
-    m.process(None, [{k: v.to(DEV) for k, v in s.items()} for s in samples])  # bincounts on the device
-    got = m.evaluate()
-    want = json.loads(str(g['occupancy_json']))
-    for k in want:
-        assert abs(got[k] - want[k]) <= 1e-12, (k, got[k], want[k])
-
-
 def test_detector_loss_is_invariant_to_the_row_order(monkeypatch):
     """ESB200_ROW_ORDER=morton: same voxels and features in Z-ordered rows -> the same losses (order-invariant sums)."""
     monkeypatch.setenv('ESB200_ROW_ORDER', 'morton')
@@ -292,21 +309,6 @@ def test_detector_loss_is_invariant_to_the_row_order(monkeypatch):
         assert rel(losses[k], g[f'b_{k}']) <= 1e-3, (k, float(losses[k]), float(g[f'b_{k}']))
 
 
-def test_detector_loss_with_active_pruning_matches_reference():
-    g = load('detector_g1')
-    cfg = det_config()
-    cfg['bbox_head']['pts_prune_threshold'] = int(g['c_prune'])
-    model, _ = product_state_dict(cfg, g, adjust_fcaf3d_head)
-    model = model.to(DEV).train()
-    batch = det_inputs(1, False)
-    data = model.data_preprocessor(dict(inputs=batch['inputs'], data_samples=batch['data_samples']), True)
-    with torch.no_grad():
-        losses = model(**data, mode='loss')
-    for k in ('loss_center', 'loss_bbox', 'loss_cls'):
-        assert rel(losses[k], g[f'c_{k}']) <= 1e-3, (k, float(losses[k]), float(g[f'c_{k}']))
-
-
-# ------------------------------------------------------------------------------------------------ experimental kernels
 @pytest.mark.xfail(strict=False, reason='conv2d_tc.cu was written without GPU access (round 1 budget spent); it is not on '
                    'the measured path (ESB200_CONV2D=tc opts in) and gets its first run here')
 def test_conv2d_tc_forward_matches_torch():
