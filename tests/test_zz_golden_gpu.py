@@ -214,7 +214,7 @@ def test_grounder_predictions_match_reference():
         assert float((ds.pred_instances_3d.bboxes_3d.tensor.cpu() - want_b).abs().max()) <= 1e-3 * float(want_b.abs().max())
 
 
-# ------------------------------------------------------------------------------------------------ continuous (f4)
+# ------------------------------------------------------------------------------------------------ metrics, pruning
 def test_grounding_and_occupancy_metrics_match_reference():
     import json
     from embodiedscan_b200.evaluation import GroundingMetric, OccupancyMetric
@@ -248,8 +248,6 @@ def test_detector_loss_with_active_pruning_matches_reference():
     for k in ('loss_center', 'loss_bbox', 'loss_cls'):
         assert rel(losses[k], g[f'c_{k}']) <= 1e-3, (k, float(losses[k]), float(g[f'c_{k}']))
 
-
-# ------------------------------------------------------------------------------------------------ experimental kernels
 
 # ---- least-proven paths last: a fault here cannot poison the CUDA context of the tests above ----
 def test_continuous_detector_loss_and_gradients_match_reference():
