@@ -154,6 +154,24 @@ def pack_ohwi(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def conv2d_tc_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw, stride: int, pad: int) -> torch.Tensor:
+    """EXPERIMENTAL: dL/dx of ``F.conv2d(x, w, stride, pad)`` with the same kernel in transposed-gather mode.
+    dy (N,Cout,Ho,Wo) bf16 channels_last; w (Cout,Cin,kh,kw); returns dx (N,Cin,H,W) bf16 channels_last."""
+    from . import _ffi
+    assert dy.is_cuda and dy.dtype == torch.bfloat16 and dy.is_contiguous(memory_format=torch.channels_last)
+    cout, cin, kh, kw = w.shape
+    H, W = in_hw
+    flat = w.detach().permute(1, 2, 3, 0).reshape(cin, -1)             # (ci | ky, kx, co)
+    r = flat.shape[1]
+    r_pad = (r + 63) // 64 * 64
+    wt = torch.zeros((cin, r_pad), dtype=torch.bfloat16, device=w.device)
+    wt[:, :r] = flat.to(torch.bfloat16)
+    dx = torch.empty((dy.shape[0], cin, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
+    _ffi.call('esb_conv2d_tc_dgrad', dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), dy.shape[0], H, W, cin, cout, kh, kw,
+              stride, pad, r_pad, _ffi.stream())
+    return dx
+
+
 def conv2d_backend() -> str:
     """'cudnn' (default, the measured path) or 'tc' (ESB200_CONV2D=tc: own tcgen05 kernel for blocks that need no
     gradient — the frozen stem-side stages in training, every block in inference)."""

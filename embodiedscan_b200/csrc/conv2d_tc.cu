@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(160)
 conv2d_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wt,
                      const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res,
                      __nv_bfloat16* __restrict__ y, long long M, int H, int W, int cin, int Ho, int Wo, int cout, int kh,
-                     int kw, int stride, int pad, int r_pad, int relu) {
+                     int kw, int stride, int pad, int r_pad, int relu, int transposed) {
   constexpr int B_STAGE_BYTES = N_TILE * 128;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int LAG = STAGES - 2;
@@ -73,8 +73,10 @@ conv2d_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
         const long long n = m / ((long long)Ho * Wo);
         const int rem = (int)(m - n * (long long)Ho * Wo);
         const int oy = rem / Wo, ox = rem - oy * Wo;
-        iy0[i] = oy * stride - pad;
-        ix0[i] = ox * stride - pad;
+        // forward: source pixel = row pixel * stride - pad + tap.  transposed (dgrad): rows are pixels of the conv's
+        // INPUT grid and the source is dy: source pixel = (row pixel + pad - tap) / stride when that division is exact.
+        iy0[i] = transposed ? oy + pad : oy * stride - pad;
+        ix0[i] = transposed ? ox + pad : ox * stride - pad;
         img_off[i] = n * (long long)H * W * cin;
       } else {
         iy0[i] = ix0[i] = 0;
@@ -92,8 +94,18 @@ conv2d_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
       const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES) + a_thread_off;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int iy = iy0[i] + ky, ix = ix0[i] + kx;
-        const bool ok = tap_ok && img_off[i] >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W;
+        int iy, ix;
+        bool ok = tap_ok && img_off[i] >= 0;
+        if (!transposed) {
+          iy = iy0[i] + ky;
+          ix = ix0[i] + kx;
+        } else {
+          const int ny = iy0[i] - ky, nx = ix0[i] - kx;
+          iy = ny / stride;
+          ix = nx / stride;
+          ok = ok && ny >= 0 && nx >= 0 && iy * stride == ny && ix * stride == nx;
+        }
+        ok = ok && iy >= 0 && iy < H && ix >= 0 && ix < W;
         const __nv_bfloat16* src = ok ? x + img_off[i] + ((long long)iy * W + ix) * cin + ch : x;
         cp_async16_ca(a_base + i * 2048, src, ok ? 16 : 0);
       }
@@ -195,23 +207,43 @@ conv2d_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 template <int N_TILE, int STAGES>
 int launch_conv2d(const void* x, const void* wt, const float* bias, const void* res, void* y, long long M, int H, int W,
                   int cin, int Ho, int Wo, int cout, int kh, int kw, int stride, int pad, int r_pad, int relu,
-                  cudaStream_t stream) {
+                  int transposed, cudaStream_t stream) {
   size_t smem = (size_t)STAGES * (A_STAGE_BYTES + N_TILE * 128) + 1024 + 256;
   auto kern = conv2d_tc_fwd_kernel<N_TILE, STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { esb_set_error("conv2d_tc_fwd: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
   dim3 grid(esb_div_up(M, TC_M), esb_div_up(cout, N_TILE));
   kern<<<grid, 160, smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)wt, bias, (const __nv_bfloat16*)res,
-                                    (__nv_bfloat16*)y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu);
+                                    (__nv_bfloat16*)y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, transposed);
   return ESB_OK;
 }
 
 }  // namespace
 
+static int conv2d_dispatch(const void* x, const void* w, const float* bias, const void* residual, void* y, long long M,
+                           int Hs, int Ws, int cs, int Hr, int Wr, int cr, int kh, int kw, int stride, int pad, int r_pad,
+                           int relu, int transposed, cudaStream_t stream) {
+  const long long row_tiles = (M + TC_M - 1) / TC_M;
+  int rc;
+#define ESB_C2D(NT, ST) \
+  launch_conv2d<NT, ST>(x, w, bias, residual, y, M, Hs, Ws, cs, Hr, Wr, cr, kh, kw, stride, pad, r_pad, relu, transposed, stream)
+  if (cr > 128 && row_tiles * ((cr + 255) / 256) >= 148)
+    rc = ESB_C2D(256, 4);
+  else if (cr > 64)
+    rc = ESB_C2D(128, 3);
+  else if (cr > 32)
+    rc = ESB_C2D(64, 4);
+  else
+    rc = ESB_C2D(32, 4);
+#undef ESB_C2D
+  if (rc != ESB_OK) return rc;
+  ESB_CUDA_LAUNCH_CHECK("conv2d_tc_fwd_kernel");
+  return ESB_OK;
+}
+
 extern "C" int esb_conv2d_tc_fwd(const void* x, const void* w_ohwi, const float* bias, const void* residual, void* y,
                                  int n_img, int H, int W, int cin, int cout, int kh, int kw, int stride, int pad,
                                  int r_pad, int relu, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
   ESB_CHECK_ARG(cin > 0 && cin % 8 == 0, "esb_conv2d_tc_fwd: Cin must be a positive multiple of 8 (16-byte pieces)");
   ESB_CHECK_ARG(cout > 0 && cout % 8 == 0, "esb_conv2d_tc_fwd: Cout must be a positive multiple of 8");
   ESB_CHECK_ARG(kh >= 1 && kw >= 1 && stride >= 1 && pad >= 0, "esb_conv2d_tc_fwd: bad filter geometry");
@@ -220,17 +252,22 @@ extern "C" int esb_conv2d_tc_fwd(const void* x, const void* w_ohwi, const float*
   ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tc_fwd: empty output");
   const long long M = (long long)n_img * Ho * Wo;
   if (M == 0) return ESB_OK;
-  const long long row_tiles = (M + TC_M - 1) / TC_M;
-  int rc;
-  if (cout > 128 && row_tiles * ((cout + 255) / 256) >= 148)
-    rc = launch_conv2d<256, 4>(x, w_ohwi, bias, residual, y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, stream);
-  else if (cout > 64)
-    rc = launch_conv2d<128, 3>(x, w_ohwi, bias, residual, y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, stream);
-  else if (cout > 32)
-    rc = launch_conv2d<64, 4>(x, w_ohwi, bias, residual, y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, stream);
-  else
-    rc = launch_conv2d<32, 4>(x, w_ohwi, bias, residual, y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, stream);
-  if (rc != ESB_OK) return rc;
-  ESB_CUDA_LAUNCH_CHECK("conv2d_tc_fwd_kernel");
-  return ESB_OK;
+  return conv2d_dispatch(x, w_ohwi, bias, residual, y, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, r_pad, relu, 0,
+                         (cudaStream_t)stream_);
+}
+
+// Input gradient of the same convolution with the SAME kernel in transposed-gather mode: rows are the pixels of the
+// conv's input grid, the source is dy (n_img,Ho,Wo,cout), and w_ihwo (cin, r_pad) holds the filter as
+// (ci | ky, kx, co), rows zero padded from kh*kw*cout to r_pad. dx (n_img,H,W,cin) is written once (no atomics).
+extern "C" int esb_conv2d_tc_dgrad(const void* dy, const void* w_ihwo, void* dx, int n_img, int H, int W, int cin,
+                                   int cout, int kh, int kw, int stride, int pad, int r_pad, void* stream_) {
+  ESB_CHECK_ARG(cin > 0 && cin % 8 == 0 && cout > 0 && cout % 8 == 0, "esb_conv2d_tc_dgrad: channels must be multiples of 8");
+  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && stride >= 1 && pad >= 0, "esb_conv2d_tc_dgrad: bad filter geometry");
+  ESB_CHECK_ARG(r_pad % 64 == 0 && r_pad >= kh * kw * cout, "esb_conv2d_tc_dgrad: r_pad must be kh*kw*Cout rounded up to 64");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tc_dgrad: empty output");
+  const long long M = (long long)n_img * H * W;
+  if (M == 0) return ESB_OK;
+  return conv2d_dispatch(dy, w_ihwo, nullptr, nullptr, dx, M, Ho, Wo, cout, H, W, cin, kh, kw, stride, pad, r_pad, 0, 1,
+                         (cudaStream_t)stream_);
 }

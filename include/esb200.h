@@ -93,6 +93,11 @@ int esb_act_bwd(const void* dy, const void* y, void* dx, long long n, int act, i
 int esb_conv2d_tc_fwd(const void* x, const void* w_ohwi, const float* bias, const void* residual, void* y, int n_img,
                       int H, int W, int cin, int cout, int kh, int kw, int stride, int pad, int r_pad, int relu,
                       void* stream);
+/* EXPERIMENTAL: input gradient of the same convolution (transposed-gather mode of the same kernel). dy
+ * (n_img,Ho,Wo,cout) bf16 NHWC; w_ihwo (cin, r_pad) bf16 = the filter as (ci | ky,kx,co), rows zero padded from
+ * kh*kw*cout to r_pad; dx (n_img,H,W,cin) bf16 NHWC, every element written once. */
+int esb_conv2d_tc_dgrad(const void* dy, const void* w_ihwo, void* dx, int n_img, int H, int W, int cin, int cout,
+                        int kh, int kw, int stride, int pad, int r_pad, void* stream);
 
 /* ---- point painting (batch_point_sample + apply_3d_transformation + batch_points_cam2img + F.grid_sample;
  * embodiedscan/models/layers/fusion_layers/point_fusion.py:208-311, structures/bbox_3d/utils.py:289-332) -------- */

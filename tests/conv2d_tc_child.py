@@ -21,7 +21,7 @@ CASES = [
 
 
 def main():
-    from embodiedscan_b200.backbones import conv2d_tc, pack_ohwi
+    from embodiedscan_b200.backbones import conv2d_tc, conv2d_tc_dgrad, pack_ohwi
     dev = 'cuda:0'
     for cin, cout, k, stride, pad, hw, n, with_res in CASES:
         g = torch.Generator().manual_seed(cin * 1000 + cout + k)
@@ -39,8 +39,21 @@ def main():
         torch.cuda.synchronize()
         err = float((out.float().cpu() - ref).abs().max())
         tol = 2e-2 * max(float(ref.abs().max()), 1.0)
-        print(json.dumps(dict(case=[cin, cout, k, stride, pad, list(hw), n, with_res], err=err, tol=tol,
+        print(json.dumps(dict(kind='fwd', case=[cin, cout, k, stride, pad, list(hw), n, with_res], err=err, tol=tol,
                               ok=bool(out.shape == ref.shape and err <= tol))), flush=True)
+        if cin == 8:
+            continue                                     # the stem is frozen: no input gradient on the path
+        # input gradient through the transposed-gather mode of the same kernel
+        xr = x.float().requires_grad_(True)
+        yr = F.conv2d(xr, w.float(), None, stride, pad)
+        dy = torch.randn(yr.shape, generator=g).bfloat16()
+        yr.backward(dy.float())
+        dx = conv2d_tc_dgrad(dy.to(dev).contiguous(memory_format=torch.channels_last), w.to(dev), hw, stride, pad)
+        torch.cuda.synchronize()
+        err = float((dx.float().cpu() - xr.grad).abs().max())
+        tol = 2e-2 * max(float(xr.grad.abs().max()), 1.0)
+        print(json.dumps(dict(kind='dgrad', case=[cin, cout, k, stride, pad, list(hw), n], err=err, tol=tol,
+                              ok=bool(dx.shape == xr.grad.shape and err <= tol))), flush=True)
 
 
 if __name__ == '__main__':
