@@ -41,6 +41,7 @@ SIGNATURES = {
     'esb_act_bwd': ('pppqiip', 'i'),
     'esb_conv2d_tc_fwd': ('ppppp' + 'iiiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tc_dgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),
+    'esb_conv2d_tc_wgrad': ('ppp' + 'iiiiiiiii' + 'p', 'i'),
     'esb_paint_meta_bytes': ('', 'i'),
     'esb_paint_fwd': ('pppqfppipiiiffppip', 'i'),
     'esb_paint_bwd': ('pppqfppipiiiffpip', 'i'),

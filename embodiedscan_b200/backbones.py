@@ -172,6 +172,39 @@ def conv2d_tc_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw, stride: int, pad: 
     return dx
 
 
+def conv2d_tc_wgrad(x: torch.Tensor, dy: torch.Tensor, w_shape, stride: int, pad: int) -> torch.Tensor:
+    """EXPERIMENTAL: dL/dw of ``F.conv2d(x, w, stride, pad)``; x (N,Cin,H,W), dy (N,Cout,Ho,Wo) bf16 channels_last ->
+    (Cout,Cin,kh,kw) fp32 (split-K partial sums accumulate through fp32 atomics)."""
+    from . import _ffi
+    cout, cin, kh, kw = w_shape
+    assert x.dtype == dy.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last) \
+        and dy.is_contiguous(memory_format=torch.channels_last)
+    dw_t = torch.zeros((kh * kw * cin, cout), dtype=torch.float32, device=x.device)
+    _ffi.call('esb_conv2d_tc_wgrad', x.data_ptr(), dy.data_ptr(), dw_t.data_ptr(), x.shape[0], x.shape[2], x.shape[3], cin,
+              cout, kh, kw, stride, pad, _ffi.stream())
+    return dw_t.view(kh, kw, cin, cout).permute(3, 2, 0, 1)
+
+
+class _Conv2dTC(torch.autograd.Function):
+    """EXPERIMENTAL (ESB200_CONV2D=tc): ``F.conv2d(x, w, None, stride, pad)`` for bf16 channels_last activations with all
+    three passes on the tcgen05 kernels of csrc/conv2d_tc.cu."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, pad):
+        ctx.save_for_backward(x, w)
+        ctx.geom = (stride, pad)
+        return conv2d_tc(x, pack_ohwi(w), None, None, False, w.shape[2], w.shape[3], stride, pad)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        stride, pad = ctx.geom
+        dy = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = conv2d_tc_dgrad(dy, w, x.shape[2:], stride, pad) if ctx.needs_input_grad[0] else None
+        dw = conv2d_tc_wgrad(x, dy, w.shape, stride, pad).to(w.dtype) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None
+
+
 def conv2d_backend() -> str:
     """'cudnn' (default, the measured path) or 'tc' (ESB200_CONV2D=tc: own tcgen05 kernel for blocks that need no
     gradient — the frozen stem-side stages in training, every block in inference)."""
@@ -235,7 +268,12 @@ class _ConvBN(nn.Module):
                 if not conv.weight.requires_grad:
                     self._const_w['ohwi'] = wp
             return conv2d_tc(x, wp, b, res, relu, w.shape[2], w.shape[3], conv.stride[0], conv.padding[0])
-        y = F.conv2d(x, w, None, conv.stride, conv.padding)
+        if (conv2d_backend() == 'tc' and x.is_cuda and x.dtype == torch.bfloat16 and w.shape[1] % 8 == 0
+                and w.shape[0] % 8 == 0 and x.is_contiguous(memory_format=torch.channels_last)
+                and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]):
+            y = _Conv2dTC.apply(x, w, conv.stride[0], conv.padding[0])       # trainable block: all three passes
+        else:
+            y = F.conv2d(x, w, None, conv.stride, conv.padding)
         if y.is_cuda and y.shape[1] % 8 == 0 and y.is_contiguous(memory_format=torch.channels_last):
             return _BiasResAct.apply(y, b, res, SP.ACT_RELU if relu else SP.ACT_NONE)   # bias + residual + ReLU fused
         y = y + b.to(y.dtype).view(1, -1, 1, 1)

@@ -218,6 +218,161 @@ int launch_conv2d(const void* x, const void* wt, const float* bias, const void* 
   return ESB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad: dW^T[r, co] += sum over output pixels m of A[m, r] * dy[m, co], r = (ky, kx, ci) — the same implicit A as the
+// forward pass, now MN-major on both sides with the PIXELS as the reduction dimension (64 per stage), exactly the
+// operand arrangement of spconv_tc_wgrad_kernel with the pair list replaced by index arithmetic.
+// CTA = (chunk of pixels: split-K) x (128-wide slice of r) x (N_TILE slice of Cout); fp32 atomics into dW^T.
+// ------------------------------------------------------------------------------------------------------------
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(160)
+conv2d_tc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw,
+                       long long M, int H, int W, int cin, int Ho, int Wo, int cout, int kh, int kw, int stride, int pad,
+                       int chunk_pixels) {
+  constexpr int A_BYTES = 64 * 256;              // 64 pixels x 128 reduction elements (2 M-atoms of 64)
+  constexpr int B_BYTES = 64 * N_TILE * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int LAG = STAGES - 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const long long s_beg = (long long)blockIdx.x * chunk_pixels;
+  const long long s_end = s_beg + chunk_pixels < M ? s_beg + chunk_pixels : M;
+  if (s_beg >= M) return;                          // uniform for the whole CTA
+  const int total = (int)((s_end - s_beg + 63) / 64);
+  const int R = kh * kw * cin;
+  const int r0 = blockIdx.y * 128, co0 = blockIdx.z * N_TILE;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, N_TILE);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    const int t = threadIdx.x;
+    // thread t moves 16-byte piece (t & 15) of pixel rows kk = (t >> 4) + 8 q, q = 0..7; its 8 reduction elements
+    // r = r0 + 8 (t & 15) .. +7 lie in ONE filter tap (cin % 8 == 0), fixed for the whole kernel
+    const int mc = t & 15, kk0 = t >> 4;
+    const int r = r0 + mc * 8;
+    const int tap = r / cin, ch = r - tap * cin;
+    const int ky = tap / kw, kx = tap - ky * kw;
+    const bool r_ok = r < R;
+    const long long HoWo = (long long)Ho * Wo;
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+      const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+      const uint32_t b_base = a_base + A_BYTES;
+      const long long m0 = s_beg + (long long)it * 64;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int kk = kk0 + 8 * q;
+        const long long m = m0 + kk;
+        bool ok = r_ok && m < s_end;
+        const __nv_bfloat16* src = x;
+        if (ok) {
+          const long long n = m / HoWo;
+          const int rem = (int)(m - n * HoWo);
+          const int oy = rem / Wo, ox = rem - oy * Wo;
+          const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+          ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+          if (ok) src = x + ((n * H + iy) * (long long)W + ix) * cin + ch;
+        }
+        // canonical MN-major SW128: atom(mi, kj) at mi*8192 + kj*1024, row kk%8, 16 B chunk index ^ row
+        const uint32_t dst = a_base + (mc >> 3) * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + (((mc & 7) ^ (kk & 7)) << 4);
+        cp_async16_cg(dst, src, ok ? 16 : 0);
+      }
+#pragma unroll
+      for (int q = 0; q < N_TILE / 16; ++q) {
+        const int idx = q * 128 + t;
+        const int kk = idx / (N_TILE / 8), nc = idx % (N_TILE / 8);
+        const long long m = m0 + kk;
+        const bool ok = m < s_end && co0 + nc * 8 < cout;
+        const uint32_t dst = b_base + (nc >> 3) * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + (((nc & 7) ^ (kk & 7)) << 4);
+        cp_async16_cg(dst, ok ? dy + m * cout + co0 + nc * 8 : dy, ok ? 16 : 0);
+      }
+      cp_async_commit();
+      if (it >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(&full_bar[(it - LAG) % STAGES]);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int d = (total > LAG ? total - LAG : 0); d < total; ++d) mbar_arrive(&full_bar[d % STAGES]);
+
+    // epilogue: TMEM lane = reduction element r (within the 128 slice), column = co
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int rr = r0 + threadIdx.x;
+    float* dwrow = dw + (long long)rr * cout + co0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (rr < R) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (co0 + c0 + i < cout) atomicAdd(dwrow + c0 + i, __uint_as_float(v[i]));
+      }
+    }
+    tc_fence_before();
+  } else {
+    const uint32_t idesc = make_idesc(128, N_TILE, 1, 1);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&full_bar[s], (it / STAGES) & 1);
+      tc_fence_after();
+      if ((threadIdx.x & 31) == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)              // 16 pixels per MMA = two 8-row K groups = 2048 B
+          umma_bf16(tmem_base, make_desc(a_addr + kk * 2048, 8192, 1024), make_desc(b_addr + kk * 2048, 8192, 1024),
+                    idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (it == total - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, N_TILE);
+  }
+}
+
+template <int N_TILE, int STAGES>
+int launch_conv2d_wgrad(const void* x, const void* dy, float* dw, long long M, int H, int W, int cin, int Ho, int Wo,
+                        int cout, int kh, int kw, int stride, int pad, int chunk_pixels, cudaStream_t stream) {
+  size_t smem = (size_t)STAGES * (64 * 256 + 64 * N_TILE * 2) + 1024 + 256;
+  auto kern = conv2d_tc_wgrad_kernel<N_TILE, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { esb_set_error("conv2d_tc_wgrad: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
+  dim3 grid(esb_div_up(M, chunk_pixels), esb_div_up(kh * kw * cin, 128), esb_div_up(cout, N_TILE));
+  kern<<<grid, 160, smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, M, H, W, cin, Ho, Wo, cout, kh,
+                                    kw, stride, pad, chunk_pixels);
+  return ESB_OK;
+}
+
 }  // namespace
 
 static int conv2d_dispatch(const void* x, const void* w, const float* bias, const void* residual, void* y, long long M,
@@ -270,4 +425,30 @@ extern "C" int esb_conv2d_tc_dgrad(const void* dy, const void* w_ihwo, void* dx,
   if (M == 0) return ESB_OK;
   return conv2d_dispatch(dy, w_ihwo, nullptr, nullptr, dx, M, Ho, Wo, cout, H, W, cin, kh, kw, stride, pad, r_pad, 0, 1,
                          (cudaStream_t)stream_);
+}
+
+// Weight gradient: dw_t (kh*kw*cin, cout) fp32, ZEROED BY THE CALLER (split-K partial sums arrive through fp32 atomics),
+// row r = (ky, kx, ci) like the forward's reduction index: dW[co, ci, ky, kx] = dw_t[(ky*kw + kx)*cin + ci, co].
+extern "C" int esb_conv2d_tc_wgrad(const void* x, const void* dy, float* dw_t, int n_img, int H, int W, int cin, int cout,
+                                   int kh, int kw, int stride, int pad, void* stream_) {
+  ESB_CHECK_ARG(cin > 0 && cin % 8 == 0 && cout > 0 && cout % 8 == 0, "esb_conv2d_tc_wgrad: channels must be multiples of 8");
+  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && stride >= 1 && pad >= 0, "esb_conv2d_tc_wgrad: bad filter geometry");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tc_wgrad: empty output");
+  const long long M = (long long)n_img * Ho * Wo;
+  if (M == 0) return ESB_OK;
+  const int n_tile = cout > 64 ? 128 : 64;
+  // ~4 waves of 2 CTAs per SM over the (r-slice, channel-tile) grid; chunks of whole 64-pixel stages
+  const long long tiles = (long long)esb_div_up(kh * kw * cin, 128) * esb_div_up(cout, n_tile);
+  const long long target_chunks = (4LL * 296 + tiles - 1) / tiles;
+  long long cp = (M + target_chunks - 1) / target_chunks;
+  cp = (cp + 63) / 64 * 64;
+  if (cp < 512) cp = 512;
+  if (cp > 65536) cp = 65536;
+  int rc = n_tile == 128
+               ? launch_conv2d_wgrad<128, 3>(x, dy, dw_t, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, (int)cp, (cudaStream_t)stream_)
+               : launch_conv2d_wgrad<64, 4>(x, dy, dw_t, M, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, (int)cp, (cudaStream_t)stream_);
+  if (rc != ESB_OK) return rc;
+  ESB_CUDA_LAUNCH_CHECK("conv2d_tc_wgrad_kernel");
+  return ESB_OK;
 }

@@ -98,6 +98,10 @@ int esb_conv2d_tc_fwd(const void* x, const void* w_ohwi, const float* bias, cons
  * kh*kw*cout to r_pad; dx (n_img,H,W,cin) bf16 NHWC, every element written once. */
 int esb_conv2d_tc_dgrad(const void* dy, const void* w_ihwo, void* dx, int n_img, int H, int W, int cin, int cout,
                         int kh, int kw, int stride, int pad, int r_pad, void* stream);
+/* EXPERIMENTAL: weight gradient (pixels are the reduction dimension, split over CTAs). dw_t (kh*kw*cin, cout) fp32,
+ * zeroed by the caller, row r = (ky,kx,ci): dW[co,ci,ky,kx] = dw_t[(ky*kw+kx)*cin+ci, co]. */
+int esb_conv2d_tc_wgrad(const void* x, const void* dy, float* dw_t, int n_img, int H, int W, int cin, int cout, int kh,
+                        int kw, int stride, int pad, void* stream);
 
 /* ---- point painting (batch_point_sample + apply_3d_transformation + batch_points_cam2img + F.grid_sample;
  * embodiedscan/models/layers/fusion_layers/point_fusion.py:208-311, structures/bbox_3d/utils.py:289-332) -------- */

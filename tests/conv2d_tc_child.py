@@ -21,7 +21,7 @@ CASES = [
 
 
 def main():
-    from embodiedscan_b200.backbones import conv2d_tc, conv2d_tc_dgrad, pack_ohwi
+    from embodiedscan_b200.backbones import conv2d_tc, conv2d_tc_dgrad, conv2d_tc_wgrad, pack_ohwi
     dev = 'cuda:0'
     for cin, cout, k, stride, pad, hw, n, with_res in CASES:
         g = torch.Generator().manual_seed(cin * 1000 + cout + k)
@@ -54,6 +54,15 @@ def main():
         tol = 2e-2 * max(float(xr.grad.abs().max()), 1.0)
         print(json.dumps(dict(kind='dgrad', case=[cin, cout, k, stride, pad, list(hw), n], err=err, tol=tol,
                               ok=bool(dx.shape == xr.grad.shape and err <= tol))), flush=True)
+        # weight gradient (pixels are the reduction dimension)
+        wr = w.float().requires_grad_(True)
+        F.conv2d(x.float(), wr, None, stride, pad).backward(dy.float())
+        dw = conv2d_tc_wgrad(xd, dy.to(dev).contiguous(memory_format=torch.channels_last), tuple(w.shape), stride, pad)
+        torch.cuda.synchronize()
+        err = float((dw.float().cpu() - wr.grad).abs().max())
+        tol = 2e-2 * max(float(wr.grad.abs().max()), 1.0)
+        print(json.dumps(dict(kind='wgrad', case=[cin, cout, k, stride, pad, list(hw), n], err=err, tol=tol,
+                              ok=bool(tuple(dw.shape) == tuple(wr.grad.shape) and err <= tol))), flush=True)
 
 
 if __name__ == '__main__':

@@ -219,3 +219,12 @@ def test_conv2d_tc_index_arithmetic_forward_and_transposed():
                                 True)
         want = xr.grad.permute(0, 2, 3, 1).reshape(-1, cin).numpy()
         assert np.abs(dx - want).max() <= 1e-3 * max(np.abs(want).max(), 1), ('dgrad', cin, cout, k, stride)
+        # wgrad: dW^T[r, co] = sum_m A[m, r] dy[m, co] with the forward's implicit A, unpacked like conv2d_tc_wgrad
+        wr = w.clone().requires_grad_(True)
+        F.conv2d(x, wr, None, stride, pad).backward(dy)
+        eye = np.eye(wp.shape[1], dtype=np.float32)                       # identity weights expose A itself
+        A = _emulate_conv2d_tc(x.permute(0, 2, 3, 1).numpy(), eye, n, H, W, cin, Ho, Wo, wp.shape[1], k, k, stride, pad,
+                               wp.shape[1], False)
+        dw_t = A.T @ dy.permute(0, 2, 3, 1).reshape(-1, cout).numpy()
+        dw = torch.from_numpy(dw_t[:k * k * cin]).view(k, k, cin, cout).permute(3, 2, 0, 1)
+        assert float((dw - wr.grad).abs().max()) <= 1e-3 * max(float(wr.grad.abs().max()), 1), ('wgrad', cin, cout, k)

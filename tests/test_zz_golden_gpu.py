@@ -325,6 +325,6 @@ def test_conv2d_tc_forward_matches_torch():
         proc.communicate()
         pytest.fail('conv2d_tc child timed out (kernel hang?)')
     lines = [json.loads(l) for l in out.splitlines() if l.startswith('{')]
-    assert proc.returncode == 0 and len(lines) == 13, (proc.returncode, out[-2000:], err[-2000:])
+    assert proc.returncode == 0 and len(lines) == 19, (proc.returncode, out[-2000:], err[-2000:])
     bad = [l for l in lines if not l['ok']]
     assert not bad, bad
