@@ -15,6 +15,9 @@
 // is 3 chunks instead of 9. Same warp roles as spconv_tc.cu: warps 0-3 gather then run the epilogue (TMEM lane =
 // pixel), warp 4 allocates TMEM and issues tcgen05.mma; full/empty mbarrier ring, tcgen05.commit frees stages.
 //
+// The input gradient is the same kernel in transposed-gather mode; the weight gradient is a second kernel below with
+// the pixels as the reduction dimension (split-K).
+//
 // Roofline: HBM. Algorithmic bytes per image = (H*W*Cin + Ho*Wo*Cout [+ residual]) * 2 + R_pad*Cout*2.
 #include "tc_common.cuh"
 
