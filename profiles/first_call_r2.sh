@@ -23,6 +23,13 @@ for tag in ('input', 'morton'):
     except Exception as e:
         print(tag, 'failed:', e)
 PY
+# 4. the experimental conv2d family on its own (JSON line per case), then the bench with it switched in
+timeout 300 python tests/conv2d_tc_child.py > gpurun_out/r2_conv2d_cases.jsonl 2> gpurun_out/r2_conv2d_cases.log
+grep -c '"ok": true' gpurun_out/r2_conv2d_cases.jsonl; grep '"ok": false' gpurun_out/r2_conv2d_cases.jsonl | head -5
+if ! grep -q '"ok": false' gpurun_out/r2_conv2d_cases.jsonl && [ -s gpurun_out/r2_conv2d_cases.jsonl ]; then
+  ESB200_CONV2D=tc timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_conv2d_tc.json 2> gpurun_out/r2_bench_conv2d_tc.log
+  tail -c 600 gpurun_out/r2_bench_conv2d_tc.json
+fi
 export ESB_CUDA_PROFILER_RANGE=1
 for order in input morton; do
   timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
