@@ -228,3 +228,47 @@ def test_conv2d_tc_index_arithmetic_forward_and_transposed():
         dw_t = A.T @ dy.permute(0, 2, 3, 1).reshape(-1, cout).numpy()
         dw = torch.from_numpy(dw_t[:k * k * cin]).view(k, k, cin, cout).permute(3, 2, 0, 1)
         assert float((dw - wr.grad).abs().max()) <= 1e-3 * max(float(wr.grad.abs().max()), 1), ('wgrad', cin, cout, k)
+
+
+def test_continuous_occupancy_view_prefix_painting_control_flow(monkeypatch):
+    """EmbodiedOccPredictor.extract_feat with the CUDA pieces replaced by recorders: prefix idx paints the whole prior
+    grid from feat2d[:idx+1] with its own projection prefix; volumes are stacked per prefix and fused with the sparse
+    volume of the same batch size."""
+    import types
+
+    import embodiedscan_b200.occupancy as O
+    n_prefix, V, C2d, C3d = 3, 3, 6, 5
+    n_vox = [4, 4, 2]
+    calls = []
+
+    def fake_paint(feat, pts, batch, metas, proj, pad_hw, n_views):
+        assert feat.is_contiguous(memory_format=torch.channels_last) and feat.shape[0] == n_views and batch is None
+        assert proj.shape == (1, n_views, 4, 4) and proj.is_contiguous() and pts.shape == (32, 3)
+        calls.append((n_views, int(metas[0])))
+        return torch.full((pts.shape[0], feat.shape[1]), float(n_views))
+    monkeypatch.setattr(O, 'paint_float_points', fake_paint)
+    monkeypatch.setattr(O, 'pack_paint_metas', lambda ms, dev: torch.tensor([ms[0]['tag']]))
+    monkeypatch.setattr(O, 'pack_projections', lambda ms, ct, dev: torch.zeros(1, V, 4, 4))
+    m = O.EmbodiedOccPredictor.__new__(O.EmbodiedOccPredictor)
+    torch.nn.Module.__init__(m)
+    m.compute_dtype, m.coord_type, m.n_voxels = torch.float32, 'DEPTH', n_vox
+    m.backbone = lambda x: x
+    m.neck = lambda x: [torch.randn(V, C2d, 8, 8).contiguous(memory_format=torch.channels_last)]
+    m.prior_generator = types.SimpleNamespace(grid_anchors=lambda sizes, device: [torch.rand(32, 7)])
+    seen = {}
+
+    def fake_sparse(points, prior):
+        seen['n'] = [p.shape[0] for p in points]
+        return torch.ones(len(points), C3d, *n_vox)
+    m.sparse_volume = fake_sparse
+    m.neck_3d = lambda x: [x]
+    samples = [types.SimpleNamespace(metainfo=dict(tag=20 + i, depth2img=dict(origin=[0.1, 0.2, 0.3])))
+               for i in range(n_prefix)]
+    feats, valid = m.extract_feat(dict(points=[[torch.zeros(5 * (i + 1), 3)] for i in range(n_prefix)],
+                                       imgs=torch.zeros(1, V, 3, 32, 32)), samples)
+    assert calls == [(1, 20), (2, 21), (3, 22)] and seen['n'] == [5, 10, 15]
+    fused = feats[0]
+    assert fused.shape == (n_prefix, C2d + C3d, *n_vox) and valid.shape == (n_prefix, 1, *n_vox)
+    for i in range(n_prefix):
+        assert float(fused[i, :C2d].min()) == float(fused[i, :C2d].max()) == float(i + 1)
+    assert float(fused[:, C2d:].min()) == 1.0 and float(valid.min()) == 1.0
