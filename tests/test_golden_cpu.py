@@ -573,3 +573,25 @@ def test_grounding_box_coders_match_reference(coder, nreg):
     assert float((got[..., :6] - want[..., :6]).abs().max()) <= 1e-5
     dang = torch.remainder(got[..., 6:] - want[..., 6:] + np.pi, 2 * np.pi) - np.pi
     assert float(dang.abs().max()) <= 1e-5
+
+
+def test_reference_checkpoint_loader(tmp_path):
+    """An mmengine-style checkpoint file with the REFERENCE's parameter names (manifest read off its own modules), a DDP
+    `module.` prefix and no num_batches_tracked buffers loads strictly into the product detector."""
+    from embodiedscan_b200 import MODELS
+    from embodiedscan_b200.checkpoint import load_reference_checkpoint
+    g = load('detector_g1')
+    ref_sd = adjust_fcaf3d_head(fill_state_dict(manifest(g)))
+    ckpt = dict(meta=dict(epoch=12), state_dict={'module.' + k: v for k, v in ref_sd.items()
+                                                 if not k.endswith('num_batches_tracked')}, optimizer=dict())
+    path = str(tmp_path / 'mv-3ddet.pth')
+    torch.save(ckpt, path)
+    model = MODELS.build(det_config())
+    missing, unexpected = load_reference_checkpoint(model, path)
+    assert missing == [] and unexpected == []
+    sd = model.state_dict()
+    assert torch.equal(sd['backbone.layer1.0.cb1.conv.weight'], ref_sd['backbone.layer1.0.conv1.weight'])
+    assert torch.equal(sd['backbone_3d.layer2.0.conv1.kernel'], ref_sd['backbone_3d.layer2.0.conv1.kernel'])
+    bad = dict(state_dict={k: v for k, v in ref_sd.items() if 'conv_cls' not in k})
+    with pytest.raises(RuntimeError, match='missing'):
+        load_reference_checkpoint(MODELS.build(det_config()), bad)
