@@ -4,9 +4,10 @@ README.md:206 of the reference) into the esb200 modules.
 mmengine saves ``{'meta': ..., 'state_dict': {...}, 'optimizer': ...}``; keys may carry a ``module.`` prefix from
 DistributedDataParallel. The esb200 modules keep the reference's parameter names and shapes (ME ``kernel`` (K,Cin,Cout) /
 (Cin,Cout), ``bias`` (1,Cout), ``.bn.*``; mmdet ``conv1 / bn1 / layerX.Y.convZ / downsample.N`` are mapped on load by
-``backbones.ResNet._load_from_state_dict``), so no tensor is reshaped or transposed here — which also fixes the kernel
-offset enumeration of a trained checkpoint to the x-fastest order the kernels use (the order MinkowskiEngine's
-hypercube region iterator produces, †upstream).
+``backbones.ResNet._load_from_state_dict``), so no tensor is reshaped or transposed here. One assumption rides on
+that (unpinned without MinkowskiEngine): slice k of a trained ``kernel`` belongs to the k-th offset of
+ME's hypercube region iterator, taken to be x-fastest — the enumeration the kernels and the oracle use. If a real
+checkpoint shows otherwise, the fix is one permutation of dim 0 of every 27- and 8-slice kernel here.
 """
 from typing import Dict, Tuple
 
