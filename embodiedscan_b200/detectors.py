@@ -222,6 +222,11 @@ class SparseFeatureFusionSingleStage3DDetector(nn.Module):
 
     def forward(self, inputs: Union[dict, List[dict]], data_samples=None, mode: str = 'tensor', **kwargs):
         if mode == 'loss':
+            if self.compute_dtype == torch.float32:
+                # fp32 = the parity arithmetic: library convolutions stay out of TF32 in forward AND backward
+                from .precision import fence_losses, fp32_exact
+                with fp32_exact():
+                    return fence_losses(self.loss(inputs, data_samples, **kwargs))
             return self.loss(inputs, data_samples, **kwargs)
         if mode == 'predict':
             return self.predict(inputs, data_samples, **kwargs)

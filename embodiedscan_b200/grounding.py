@@ -753,9 +753,11 @@ class SparseFeatureFusion3DGrounder(nn.Module):
         return batch_data_samples
 
     def forward(self, inputs, data_samples=None, mode='tensor', **kwargs):
-        if self.compute_dtype == torch.float32 and torch.backends.cudnn.allow_tf32:
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                return self._forward(inputs, data_samples, mode, **kwargs)
+        if self.compute_dtype == torch.float32:
+            # fp32 = the parity arithmetic: library contractions stay out of TF32 in forward AND backward
+            from .precision import fence_losses, fp32_exact
+            with fp32_exact():
+                return fence_losses(self._forward(inputs, data_samples, mode, **kwargs))
         return self._forward(inputs, data_samples, mode, **kwargs)
 
     def _forward(self, inputs, data_samples, mode, **kwargs):
