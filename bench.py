@@ -119,7 +119,9 @@ def _trainable(k, v):
     if not v.is_floating_point() or 'running_' in k or 'num_batches' in k:
         return False
     if k.startswith('backbone.'):
-        return k.endswith('.conv.weight') and not (k.startswith('backbone.stem') or k.startswith('backbone.layer1.'))
+        tail = k[len('backbone.'):]
+        is_conv = tail.endswith('.weight') and ('.conv' in tail or '.downsample.0' in tail) and tail.startswith('layer')
+        return is_conv and not tail.startswith('layer1.')      # stem (conv1/bn1) + stage 1 frozen, BNs in eval
     return True
 
 

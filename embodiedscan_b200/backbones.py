@@ -346,6 +346,7 @@ class ResNet(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
         self._freeze()
+        self._register_state_dict_hook(ResNet._rename_hook)
 
     def _freeze(self):
         if not self.norm_requires_grad:
@@ -383,19 +384,24 @@ class ResNet(nn.Module):
                 outs.append(x)
         return tuple(outs)
 
-    # checkpoint compatibility with mmdet / torchvision parameter names
-    def state_dict(self, *args, **kwargs):
-        sd = super().state_dict(*args, **kwargs)
-        out = type(sd)()
-        for k, v in sd.items():
-            for a, b in _RENAME.items():
-                k = k.replace(a, b)
-            out[k] = v
-        return out
+    # checkpoint compatibility with mmdet / torchvision parameter names: a state-dict hook (not a `state_dict` override,
+    # which nn.Module ignores for nested modules) so `detector.state_dict()` carries `backbone.layer1.0.conv1.weight`
+    @staticmethod
+    def _rename_hook(module, sd, prefix, local_metadata):
+        items = list(sd.items())
+        sd.clear()                                   # rebuilt in place so the key order is kept
+        for k, v in items:
+            if k.startswith(prefix):
+                tail = k[len(prefix):]
+                for a, b in _RENAME.items():
+                    tail = tail.replace(a, b)
+                k = prefix + tail
+            sd[k] = v
+        return sd
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         inv = {b: a for a, b in _RENAME.items() if not a.startswith('stem.')}     # stem handled explicitly below
-        own = {k for k in super().state_dict(prefix=prefix).keys()}
+        own = {prefix + k for k, _ in list(self.named_parameters()) + list(self.named_buffers())}
         for k in list(state_dict.keys()):
             if not k.startswith(prefix) or k in own:
                 continue

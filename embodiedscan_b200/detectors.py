@@ -186,6 +186,8 @@ class SparseFeatureFusionSingleStage3DDetector(nn.Module):
             main = torch.cuda.current_stream()
             if self._side_stream is None or self._side_stream.device != img4.device:
                 self._side_stream = torch.cuda.Stream(device=img4.device)
+                from .engine import register_grad_stream
+                register_grad_stream(self._side_stream)   # its backward writes 2D-backbone gradients into the arena
             side = self._side_stream
             side.wait_stream(main)
             with torch.cuda.stream(side):

@@ -16,6 +16,14 @@ from ._ffi import call, ptr, stream
 
 ALIGN = 16   # elements
 
+# CUDA streams other than the default one on which kernels write gradients into the arena (the detector's 2D side stream
+# registers itself here): a bucket's all-reduce must be ordered after ALL of them, not just the stream its last hook ran on.
+GRAD_STREAMS = set()
+
+
+def register_grad_stream(s):
+    GRAD_STREAMS.add(s)
+
 
 class FlatArena:
     """All trainable parameters live in ONE contiguous fp32 buffer, their gradients in another (same offsets)."""
@@ -65,6 +73,7 @@ class FlatArena:
     def zero_grad(self):
         self.grad.zero_()
         for p, o in zip(self.params, self.offsets):  # autograd may have replaced .grad; re-point it at the arena
+            p._esb_uses = 0
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
 
@@ -78,6 +87,7 @@ class DataParallelReducer:
         self.pending = [0] * len(arena.buckets)
         self.handles = []
         self.launched = [False] * len(arena.buckets)
+        self.enabled = True              # tests switch the collective off to take single-rank gradients
         if self.world > 1:
             for i, p in enumerate(arena.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(arena.bucket_of[i]))
@@ -87,14 +97,28 @@ class DataParallelReducer:
         self.pending = list(self.arena.n_params_in_bucket)
         self.launched = [False] * len(self.arena.buckets)
         self.handles = []
+        self.seen = set()
 
     def _launch(self, b):
         s, e = self.arena.buckets[b]
+        if self.arena.grad.is_cuda:
+            # NCCL orders the collective after the CURRENT stream only. A bucket can hold gradients written on several
+            # streams (3D branch on the main stream, 2D backbone on the side stream): by the time the last hook fires every
+            # producing kernel has been enqueued, so waiting on each producer stream here is sufficient.
+            cur = torch.cuda.current_stream()
+            for st in [torch.cuda.default_stream()] + list(GRAD_STREAMS):
+                if st != cur:
+                    cur.wait_stream(st)
         self.handles.append(dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.launched[b] = True
 
     def _make_hook(self, b):
         def hook(_p):
+            if not self.enabled:
+                return
+            if id(_p) in self.seen:          # a module used twice in one step fires its (manual) hook twice
+                return
+            self.seen.add(id(_p))
             self.pending[b] -= 1
             if self.pending[b] == 0 and not self.launched[b]:
                 self._launch(b)
@@ -102,7 +126,7 @@ class DataParallelReducer:
 
     def finish(self):
         """Reduce whatever was not launched by hooks (parameters unused this step), then wait."""
-        if self.world > 1:
+        if self.world > 1 and self.enabled:
             for b in range(len(self.arena.buckets)):
                 if not self.launched[b]:
                     self._launch(b)

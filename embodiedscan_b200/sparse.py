@@ -44,6 +44,23 @@ def _timed_conv_call(kind, kmap, cin, cout, dtype, *args):
     CONV_PROFILE['records'].append((kind, kmap.pairs[2], kmap.K, cin, cout, dtype, e0, e1))
 
 
+def _count_use(*params):
+    """Forward side of the 'direct' gradient path: a parameter used n times in one step gets its hooks fired after the
+    n-th backward contribution (what autograd's AccumulateGrad does for ordinary parameters)."""
+    for p in params:
+        if p is not None and getattr(p, '_esb_grad_direct', False):
+            p._esb_uses = getattr(p, '_esb_uses', 0) + 1
+
+
+def _fire_grad_hooks(*params):
+    for p in params:
+        left = getattr(p, '_esb_uses', 1) - 1
+        p._esb_uses = max(left, 0)
+        if left <= 0:
+            for hook in (getattr(p, '_post_accumulate_grad_hooks', None) or {}).values():
+                hook(p)       # what autograd's AccumulateGrad would have fired (bucket all-reduce bookkeeping)
+
+
 def _offsets(kernel_size: int, scale: int) -> List[int]:
     """Kernel offsets (x fastest) in voxel units, multiplied by the input tensor stride."""
     if kernel_size == 1:
@@ -270,6 +287,8 @@ class _SparseConv(torch.autograd.Function):
                              ptr(y), kmap.n_out, cin, cout, K, 0, 0, _ffi.dtype_code(x.dtype), stream())
         ctx.save_for_backward(x, w)
         ctx.kmap, ctx.cin, ctx.cout, ctx.wshape, ctx.tc, ctx.weight = kmap, cin, cout, weight.shape, tc, weight
+        if ctx.needs_input_grad[1]:
+            _count_use(weight)
         return y
 
     @staticmethod
@@ -301,8 +320,7 @@ class _SparseConv(torch.autograd.Function):
                 _timed_conv_call('wgrad', kmap, cin, cout, x.dtype, 'esb_spconv_wgrad', ptr(x), ptr(dy), ptr(pin),
                                  ptr(pout), ptr(koff), ptr(dw), tot, cin, cout, kmap.K, code, stream())
             if direct:
-                for hook in (getattr(weight, '_post_accumulate_grad_hooks', None) or {}).values():
-                    hook(weight)       # what autograd's AccumulateGrad would have fired (bucket all-reduce bookkeeping)
+                _fire_grad_hooks(weight)
                 dw = None
             else:
                 dw = dw.view(ctx.wshape)
@@ -355,6 +373,8 @@ class _SegNorm(torch.autograd.Function):
         ctx.meta = (S, max_rows, act, res is not None, gamma.shape if gamma is not None else None,
                     beta.shape if beta is not None else None)
         ctx.params = (gamma, beta)
+        if S == 1 and gamma is not None and beta is not None and ctx.needs_input_grad[2]:
+            _count_use(gamma, beta)
         return y
 
     @staticmethod
@@ -376,9 +396,7 @@ class _SegNorm(torch.autograd.Function):
         call('esb_norm_bwd', ptr(x), ptr(y), ptr(dy), ptr(seg_off), ptr(row_seg), S, N, max_rows, C, ptr(mean), ptr(rstd),
              ptr(g), act, ptr(sg), ptr(sgx), ptr(dx), ptr(dres), 0 if direct else 1, _ffi.dtype_code(x.dtype), stream())
         if direct:
-            for prm in (gamma, beta):
-                for hook in (getattr(prm, '_post_accumulate_grad_hooks', None) or {}).values():
-                    hook(prm)
+            _fire_grad_hooks(gamma, beta)
             return dx, dres, None, None, None, None, None, None, None, None, None, None, None
         if S == 1:       # BatchNorm: the (1,C) sums ARE the parameter gradients (no reduction kernel)
             dgamma = sgx.view(gshape) if gshape is not None else None

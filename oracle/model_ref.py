@@ -31,30 +31,32 @@ def preprocess_imgs(imgs_u8: torch.Tensor, mean, std, bgr_to_rgb=True, divisor=3
 
 
 # ------------------------------------------------------------------------------------------------ 2D backbone
-def _cb(sd, p, x, stride, padding, relu):
-    y = F.conv2d(x, sd[p + '.conv.weight'], None, stride, padding)
-    y = F.batch_norm(y, sd[p + '.bn.running_mean'], sd[p + '.bn.running_var'], sd[p + '.bn.weight'], sd[p + '.bn.bias'],
+def _cb(sd, conv, bn, x, stride, padding, relu):
+    """conv -> eval BatchNorm (-> ReLU); `conv` / `bn` are the mmdet / torchvision module names of the state dict."""
+    y = F.conv2d(x, sd[conv + '.weight'], None, stride, padding)
+    y = F.batch_norm(y, sd[bn + '.running_mean'], sd[bn + '.running_var'], sd[bn + '.weight'], sd[bn + '.bias'],
                      False, 0., 1e-5)
     return F.relu(y) if relu else y
 
 
 def resnet2d(sd, prefix, depth, x):
     kind, blocks = ARCH2D[depth]
-    x = _cb(sd, prefix + 'stem', x, 2, 3, True)
+    x = _cb(sd, prefix + 'conv1', prefix + 'bn1', x, 2, 3, True)
     x = F.max_pool2d(x, 3, 2, 1)
     outs = []
     for i, nb in enumerate(blocks):
         for j in range(nb):
             p = f'{prefix}layer{i + 1}.{j}.'
             stride = (1, 2, 2, 2)[i] if j == 0 else 1
-            idt = _cb(sd, p + 'ds', x, stride, 0, False) if (p + 'ds.conv.weight') in sd else x
+            idt = _cb(sd, p + 'downsample.0', p + 'downsample.1', x, stride, 0, False) \
+                if (p + 'downsample.0.weight') in sd else x
             if kind == 'bottleneck':
-                o = _cb(sd, p + 'cb1', x, 1, 0, True)
-                o = _cb(sd, p + 'cb2', o, stride, 1, True)
-                o = _cb(sd, p + 'cb3', o, 1, 0, False)
+                o = _cb(sd, p + 'conv1', p + 'bn1', x, 1, 0, True)
+                o = _cb(sd, p + 'conv2', p + 'bn2', o, stride, 1, True)
+                o = _cb(sd, p + 'conv3', p + 'bn3', o, 1, 0, False)
             else:
-                o = _cb(sd, p + 'cb1', x, stride, 1, True)
-                o = _cb(sd, p + 'cb2', o, 1, 1, False)
+                o = _cb(sd, p + 'conv1', p + 'bn1', x, stride, 1, True)
+                o = _cb(sd, p + 'conv2', p + 'bn2', o, 1, 1, False)
             x = F.relu(o + idt)
         outs.append(x)
     return outs

@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 import torch
 
+# state dicts carry the reference's (mmdet) names; named_parameters() the module structure's
+OWN = {'backbone.layer2.0.conv1.weight': 'backbone.layer2.0.cb1.conv.weight'}
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
@@ -32,7 +34,7 @@ def test_loss_and_gradients_match_oracle(n_scans, augment):
     model.train()
     watch = ['bbox_head.conv_cls.kernel', 'bbox_head.conv_reg.kernel', 'bbox_head.out_block_0.0.kernel',
              'bbox_head.up_block_1.0.kernel', 'backbone_3d.conv1.kernel', 'backbone_3d.layer2.0.conv1.kernel',
-             'backbone_3d.layer1.0.norm1.bn.weight', 'backbone.layer2.0.cb1.conv.weight', 'bbox_head.scales.1.scale']
+             'backbone_3d.layer1.0.norm1.bn.weight', 'backbone.layer2.0.conv1.weight', 'bbox_head.scales.1.scale']
     for k in watch:
         sd[k] = sd[k].clone().requires_grad_(True)
     ref = M.detector_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
@@ -47,7 +49,7 @@ def test_loss_and_gradients_match_oracle(n_scans, augment):
     params = dict(model.named_parameters())
     report = {}
     for k in watch:
-        g, gr = params[k].grad.cpu(), sd[k].grad
+        g, gr = params[OWN.get(k, k)].grad.cpu(), sd[k].grad
         report[k] = (float((g - gr).abs().max()) / max(float(gr.abs().max()), 1e-9),
                      float((g - gr).norm()) / max(float(gr.norm()), 1e-9))
     print('gradient parity (max-rel, l2-rel):', report)
@@ -183,7 +185,7 @@ def test_occupancy_loss_and_gradients_match_oracle():
     model.train()
     watch = ['bbox_head.occ.0.weight', 'bbox_head.occ.2.weight', 'neck_3d.down_layer_1.0.conv1.weight',
              'neck_3d.up_block_1.0.weight', 'neck.lateral_convs.0.conv.weight', 'neck.lateral_convs.3.conv.bias',
-             'backbone_3d.layer4.0.conv1.kernel', 'backbone_3d.conv1.kernel', 'backbone.layer2.0.cb1.conv.weight']
+             'backbone_3d.layer4.0.conv1.kernel', 'backbone_3d.conv1.kernel', 'backbone.layer2.0.conv1.weight']
     for k in watch:
         sd[k] = sd[k].clone().requires_grad_(True)
     ref = R.occ_loss(sd, cfg, batch['inputs']['points'], imgs, batch['data_samples'])
@@ -203,7 +205,7 @@ def test_occupancy_loss_and_gradients_match_oracle():
     params = dict(model.named_parameters())
     report = {}
     for k in watch:
-        g, gr = params[k].grad.cpu(), sd[k].grad
+        g, gr = params[OWN.get(k, k)].grad.cpu(), sd[k].grad
         report[k] = (float((g - gr).abs().max()) / max(float(gr.abs().max()), 1e-9),
                      float((g - gr).norm()) / max(float(gr.norm()), 1e-9))
     print('occupancy gradient parity (max-rel, l2-rel):', report)
@@ -268,7 +270,7 @@ def test_grounder_loss_and_gradients_match_oracle():
     watch = ['bbox_head.reg_branches.0.4.weight', 'bbox_head.cls_branches.0.bias', 'text_feat_map.weight',
              'decoder.layers.0.cross_attn.attn.in_proj_weight', 'decoder.layers.1.ffn.layers.1.weight',
              'decoder.cross_posembed.position_embedding_head.0.weight', 'neck_3d.out_block_0.0.kernel',
-             'neck_3d.up_block_2.0.kernel', 'backbone_3d.conv1.kernel', 'backbone.layer2.0.cb1.conv.weight']
+             'neck_3d.up_block_2.0.kernel', 'backbone_3d.conv1.kernel', 'backbone.layer2.0.conv1.weight']
     for k in watch:
         sd[k] = sd[k].clone().requires_grad_(True)
     for i in range(1, 3):              # shared prediction layers: every index aliases entry 0
@@ -285,7 +287,7 @@ def test_grounder_loss_and_gradients_match_oracle():
     params = dict(model.named_parameters())
     report = {}
     for k in watch:
-        g, gr = params[k].grad.cpu(), sd[k].grad
+        g, gr = params[OWN.get(k, k)].grad.cpu(), sd[k].grad
         report[k] = (float((g - gr).abs().max()) / max(float(gr.abs().max()), 1e-9),
                      float((g - gr).norm()) / max(float(gr.norm()), 1e-9))
     print('grounding gradient parity (max-rel, l2-rel):', report)
