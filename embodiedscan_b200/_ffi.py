@@ -42,6 +42,12 @@ SIGNATURES = {
     'esb_conv2d_tc_fwd': ('ppppp' + 'iiiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tc_dgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tc_wgrad': ('ppp' + 'iiiiiiiii' + 'p', 'i'),
+    'esb_conv2d_tma_fwd': ('ppppp' + 'iiiiiiiiii' + 'p', 'i'),
+    'esb_conv2d_tma_dgrad': ('ppp' + 'iiiiiiii' + 'p', 'i'),
+    'esb_conv2d_direct_fwd': ('ppppp' + 'iiiiiiiiiii' + 'p', 'i'),
+    'esb_conv2d_direct_dgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),
+    'esb_conv2d_direct_wgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),
+    'esb_maxpool2d_nhwc': ('pp' + 'iiiiiiii' + 'p', 'i'),
     'esb_paint_meta_bytes': ('', 'i'),
     'esb_paint_fwd': ('pppqfppipiiiffppip', 'i'),
     'esb_paint_bwd': ('pppqfppipiiiffpip', 'i'),

@@ -142,6 +142,48 @@ def conv2d_tc(x: torch.Tensor, w_ohwi: torch.Tensor, bias, res, relu: bool, kh: 
     return y
 
 
+def ohwi(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, kh, kw) -> contiguous (Cout, kh, kw, Cin) bf16: the filter matrix of csrc/conv_tma.cu (a channels_last
+    filter already is this memory: no copy then)."""
+    return w.detach().to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+
+
+def tma_channels_ok(c: int) -> bool:
+    return c in (16, 32, 64, 128, 256) or (c > 256 and c % 256 == 0)
+
+
+def conv2d_tma(x: torch.Tensor, w_ohwi: torch.Tensor, bias, res, relu: bool, stride: int, pad: int) -> torch.Tensor:
+    """conv + bias + residual + ReLU in ONE persistent TMA + tcgen05 launch (csrc/conv_tma.cu). x (N,Cin,H,W) bf16 in
+    channels_last memory; w_ohwi (Cout,kh,kw,Cin) bf16 from :func:`ohwi`; bias (Cout,) fp32 or None; res like the output."""
+    from . import _ffi
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    N, cin, H, W = x.shape
+    cout, kh, kw, _ = w_ohwi.shape
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    y = torch.empty((N, cout, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    if res is not None:
+        assert res.shape == y.shape and res.dtype == torch.bfloat16
+        if not res.is_contiguous(memory_format=torch.channels_last):
+            res = res.contiguous(memory_format=torch.channels_last)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    _ffi.call('esb_conv2d_tma_fwd', x.data_ptr(), w_ohwi.data_ptr(), _ffi.ptr(bias), _ffi.ptr(res), y.data_ptr(), N, H, W,
+              cin, cout, kh, kw, stride, pad, 1 if relu else 0, _ffi.stream())
+    return y
+
+
+def conv2d_tma_dgrad(dy: torch.Tensor, w_ohwi: torch.Tensor, in_hw, pad: int) -> torch.Tensor:
+    """dL/dx of a STRIDE-1 ``F.conv2d(x, w, pad)`` with the same kernel (flipped taps, filter read MN-major)."""
+    from . import _ffi
+    assert dy.is_cuda and dy.dtype == torch.bfloat16 and dy.is_contiguous(memory_format=torch.channels_last)
+    cout, kh, kw, cin = w_ohwi.shape
+    H, W = in_hw
+    dx = torch.empty((dy.shape[0], cin, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
+    _ffi.call('esb_conv2d_tma_dgrad', dy.data_ptr(), w_ohwi.data_ptr(), dx.data_ptr(), dy.shape[0], H, W, cin, cout, kh, kw,
+              pad, _ffi.stream())
+    return dx
+
+
 def pack_ohwi(w: torch.Tensor) -> torch.Tensor:
     """(Cout, Cin, kh, kw) -> (Cout, r_pad) bf16: filter taps in (ky, kx, ci) order, rows zero padded to a multiple of
     64 reduction elements — the K-major B operand of csrc/conv2d_tc.cu."""
@@ -205,11 +247,92 @@ class _Conv2dTC(torch.autograd.Function):
         return dx, dw, None, None
 
 
+class _ConvBlock2D(torch.autograd.Function):
+    """out = act(conv2d(x, w) + bias + res) of the image backbone on the library's own kernels, all three passes:
+      bf16, tensor-core channel counts -> csrc/conv_tma.cu (TMA + tcgen05; fused epilogue), its stride-1 dgrad, the
+                                         transposed-gather dgrad of csrc/conv2d_tc.cu for stride 2, tcgen05 split-K wgrad
+      fp32 (the parity arithmetic) / the 3-channel stem -> csrc/conv2d_direct.cu (fp32 FMA)
+    x channels_last; w (Cout,Cin,kh,kw) in channels_last memory (= OHWI); bias fp32 (Cout,) constant; res like the output."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, res, relu, stride, pad):
+        from . import _ffi
+        N, cin, H, W = x.shape
+        cout, _, kh, kw = w.shape
+        w_ohwi = w.detach().permute(0, 2, 3, 1)
+        if not w_ohwi.is_contiguous():
+            w_ohwi = w_ohwi.contiguous()
+        tma = x.dtype == torch.bfloat16 and tma_channels_ok(cin) and tma_channels_ok(cout)
+        if tma:
+            y = conv2d_tma(x, w_ohwi, bias, res, relu, stride, pad)
+        else:
+            Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+            y = torch.empty((N, cout, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+            if res is not None and not res.is_contiguous(memory_format=torch.channels_last):
+                res = res.contiguous(memory_format=torch.channels_last)
+            _ffi.call('esb_conv2d_direct_fwd', x.data_ptr(), w_ohwi.data_ptr(), _ffi.ptr(bias), _ffi.ptr(res), y.data_ptr(),
+                      N, H, W, cin, cout, kh, kw, stride, pad, 1 if relu else 0, _ffi.dtype_code(x.dtype), _ffi.stream())
+        ctx.save_for_backward(x, w_ohwi, y if relu else None)
+        ctx.geom = (stride, pad, relu, res is not None, tma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _ffi
+        x, w_ohwi, y = ctx.saved_tensors
+        stride, pad, relu, has_res, tma = ctx.geom
+        N, cin, H, W = x.shape
+        cout, kh, kw, _ = w_ohwi.shape
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        if relu:
+            g = torch.empty_like(y)
+            _ffi.call('esb_act_bwd', dy.data_ptr(), y.data_ptr(), g.data_ptr(), y.numel(), SP.ACT_RELU,
+                      _ffi.dtype_code(y.dtype), _ffi.stream())
+        else:
+            g = dy
+        code = _ffi.dtype_code(x.dtype)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            if tma and stride == 1:
+                dx = conv2d_tma_dgrad(g, w_ohwi, (H, W), pad)
+            elif tma:
+                dx = conv2d_tc_dgrad(g, w_ohwi.permute(0, 3, 1, 2), (H, W), stride, pad)
+            else:
+                dx = torch.empty_like(x)
+                _ffi.call('esb_conv2d_direct_dgrad', g.data_ptr(), w_ohwi.data_ptr(), dx.data_ptr(), N, H, W, cin, cout, kh,
+                          kw, stride, pad, code, _ffi.stream())
+        if ctx.needs_input_grad[1]:
+            if tma:
+                dw = conv2d_tc_wgrad(x, g, (cout, cin, kh, kw), stride, pad)          # (Cout,Cin,kh,kw) view, fp32
+            else:
+                dwo = torch.zeros((cout, kh, kw, cin), dtype=torch.float32, device=x.device)
+                _ffi.call('esb_conv2d_direct_wgrad', x.data_ptr(), g.data_ptr(), dwo.data_ptr(), N, H, W, cin, cout, kh, kw,
+                          stride, pad, code, _ffi.stream())
+                dw = dwo.permute(0, 3, 1, 2)
+            dw = dw.to(x.dtype)
+        return dx, dw, None, (g if has_res else None), None, None, None
+
+
+def maxpool2d(x: torch.Tensor, k: int, stride: int, pad: int) -> torch.Tensor:
+    """F.max_pool2d on a channels_last activation with the library's kernel when no gradient flows (the frozen stem)."""
+    if (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous(memory_format=torch.channels_last)
+            and not (torch.is_grad_enabled() and x.requires_grad)):
+        from . import _ffi
+        N, C, H, W = x.shape
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        y = torch.empty((N, C, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        _ffi.call('esb_maxpool2d_nhwc', x.data_ptr(), y.data_ptr(), N, H, W, C, k, stride, pad, _ffi.dtype_code(x.dtype),
+                  _ffi.stream())
+        return y
+    return F.max_pool2d(x, kernel_size=k, stride=stride, padding=pad)
+
+
 def conv2d_backend() -> str:
-    """'cudnn' (default, the measured path) or 'tc' (ESB200_CONV2D=tc: own tcgen05 kernel for blocks that need no
-    gradient — the frozen stem-side stages in training, every block in inference)."""
+    """'own' (default: every 2D convolution on the library's kernels, see :class:`_ConvBlock2D`) or 'cudnn'
+    (ESB200_CONV2D=cudnn: the round-1 library path, kept for A/B timing only)."""
     import os
-    return os.environ.get('ESB200_CONV2D', 'cudnn')
+    return os.environ.get('ESB200_CONV2D', 'own')
 
 
 class _ConvBN(nn.Module):
@@ -257,23 +380,20 @@ class _ConvBN(nn.Module):
             w = self._const_w.get(x.dtype)
             if w is None:
                 w = self._const_w[x.dtype] = (conv.weight.detach() * scale4).to(x.dtype)
-        if (conv2d_backend() == 'tc' and x.is_cuda and x.dtype == torch.bfloat16 and w.shape[1] % 8 == 0
-                and w.shape[0] % 8 == 0 and x.is_contiguous(memory_format=torch.channels_last)
-                and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
-                and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad
-                                                      or (res is not None and res.requires_grad)))):
-            wp = self._const_w.get('ohwi') if not conv.weight.requires_grad else None
-            if wp is None:
-                wp = pack_ohwi(w)
-                if not conv.weight.requires_grad:
-                    self._const_w['ohwi'] = wp
-            return conv2d_tc(x, wp, b, res, relu, w.shape[2], w.shape[3], conv.stride[0], conv.padding[0])
-        if (conv2d_backend() == 'tc' and x.is_cuda and x.dtype == torch.bfloat16 and w.shape[1] % 8 == 0
-                and w.shape[0] % 8 == 0 and x.is_contiguous(memory_format=torch.channels_last)
+        if (conv2d_backend() == 'own' and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and not b.requires_grad
                 and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]):
-            y = _Conv2dTC.apply(x, w, conv.stride[0], conv.padding[0])       # trainable block: all three passes
-        else:
-            y = F.conv2d(x, w, None, conv.stride, conv.padding)
+            # the library's own kernels, all three passes (conv + bias + residual + ReLU fused into one launch)
+            if not x.is_contiguous(memory_format=torch.channels_last):
+                x = x.contiguous(memory_format=torch.channels_last)
+            if w.requires_grad:
+                w = w.contiguous(memory_format=torch.channels_last)
+            else:
+                wc = self._const_w.get(('cl', x.dtype))
+                if wc is None:
+                    wc = self._const_w[('cl', x.dtype)] = w.contiguous(memory_format=torch.channels_last)
+                w = wc
+            return _ConvBlock2D.apply(x, w, b, res, relu, conv.stride[0], conv.padding[0])
+        y = F.conv2d(x, w, None, conv.stride, conv.padding)
         if y.is_cuda and y.shape[1] % 8 == 0 and y.is_contiguous(memory_format=torch.channels_last):
             return _BiasResAct.apply(y, b, res, SP.ACT_RELU if relu else SP.ACT_NONE)   # bias + residual + ReLU fused
         y = y + b.to(y.dtype).view(1, -1, 1, 1)
@@ -376,7 +496,7 @@ class ResNet(nn.Module):
 
     def forward(self, x):
         x = self.stem(x, True)
-        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+        x = maxpool2d(x, 3, 2, 1)
         outs = []
         for i in range(self.num_stages):
             x = getattr(self, f'layer{i + 1}')(x)

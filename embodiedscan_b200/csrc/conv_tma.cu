@@ -1,0 +1,403 @@
+// esb200 — dense NHWC convolution as a persistent TMA + tcgen05 implicit GEMM (bf16 in, fp32 accumulate in TMEM).
+// The per-view image backbone of the hot path (mmdet.ResNet(depth=50, base_channels=16), called at
+// embodiedscan/models/detectors/sparse_featfusion_single_stage.py:130-136; config
+// configs/detection/mv-det3d_8xb4_embodiedscan-3d-284class-9dof.py:24-34) with the frozen BatchNorm folded into the
+// weights and bias + residual + ReLU fused into the epilogue. The same kernel is the input gradient of every stride-1
+// convolution (flipped taps, weights read as the MN-major B operand: no transposed copy of the filter exists).
+//
+// GEMM view: M = output pixels, N = output channels, reduction = (filter tap, input channel).
+//   * A CTA is persistent: it walks output tiles  (TN images x TH rows x TW columns <= 128 pixels) x (N_TILE channels).
+//   * A operand: for every filter tap ONE tiled TMA load of the box {bc channels, TW, TH, TN} of the NHWC activation tensor
+//     at the tap's spatial offset. Zero padding = TMA out-of-bounds fill; stride-2 convolutions use the tensor map's element
+//     strides. The box lands in shared memory as the K-major [pixel][channel] tile tcgen05 wants; thin layers (16 / 32
+//     channels) use the 32B / 64B swizzle modes and several taps share one pipeline stage.
+//   * B operand: 2-D TMA box of the OHWI filter matrix (row = output channel, columns = (tap, input channel)).
+//   * One elected thread issues tcgen05.mma (M=128, N=N_TILE, K=16) into one of two TMEM accumulator stages, so the epilogue
+//     of tile i overlaps the loads and MMAs of tile i+1.
+//   * Epilogue warps: tcgen05.ld -> + bias (+ residual) (ReLU) -> bf16 -> swizzled shared tile -> TMA store (the store
+//     clips partial tiles; no per-thread global stores).
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp & 3).
+//
+// Roofline: HBM. Algorithmic bytes = (N*H*W*Cin + N*Ho*Wo*Cout [+ residual]) * 2 + kh*kw*Cin*Cout*2 per launch.
+#include "tc_common.cuh"
+
+using namespace esb_tc;
+
+namespace {
+
+struct ConvGeom {
+  int tiles_w, tiles_h, tiles_n, n_blocks;   // tile grid; n_blocks = Cout / N_TILE
+  int TW, TH, TN;                            // output pixels per tile along w, h, image
+  int Wo, Ho, N;                             // output extent
+  int kh, kw, stride, pad;
+  int cin, bc, nchunk, group;                // reduction channels per tap, channels per sub-tile, cin / bc, sub-tiles per stage
+  int cout, relu, flip;
+  int stages;
+};
+
+constexpr int EPI_THREADS = 128;
+constexpr int THREADS = 64 + EPI_THREADS;
+
+__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
+
+template <int N_TILE, bool B_MN>
+__global__ void __launch_bounds__(THREADS)
+conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
+                const __grid_constant__ CUtensorMap tmy, const float* __restrict__ bias,
+                const __nv_bfloat16* __restrict__ res, const ConvGeom g) {
+  constexpr int CB_COLS = N_TILE < 64 ? N_TILE : 64;          // columns per TMA store (one swizzle span)
+  constexpr int CB_ROW_BYTES = CB_COLS * 2;
+  constexpr int CB_BYTES = 128 * CB_ROW_BYTES;
+  constexpr uint32_t CB_MASK = CB_ROW_BYTES == 128 ? 7u : CB_ROW_BYTES == 64 ? 3u : 1u;
+  constexpr int B_STAGE_BYTES = N_TILE * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int TMEM_COLS = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int STAGES = g.stages;
+  uint8_t* cbuf = smem + STAGES * STAGE_BYTES;                 // 2 x CB_BYTES, 1024-aligned (STAGE_BYTES % 1024 == 0)
+  uint64_t* full_bar = (uint64_t*)(cbuf + 2 * CB_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = g.kh * g.kw;
+  const int n_sub = taps * g.nchunk;                           // sub-tiles (tap, channel chunk) per output tile
+  const int n_it = (n_sub + g.group - 1) / g.group;            // pipeline stages per output tile
+  const int bcb = g.bc * 2;                                    // bytes per sub-tile row
+  const int rows_box = g.TW * g.TH * g.TN;
+  const uint32_t a_sub_bytes = (uint32_t)rows_box * bcb;       // what TMA delivers (<= 128 rows)
+  const uint32_t b_sub_bytes = (uint32_t)N_TILE * bcb;
+  const int n_work = g.tiles_w * g.tiles_h * g.tiles_n * g.n_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmw);
+    tma_prefetch_desc(&tmy);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+        int t = work;
+        const int tw = t % g.tiles_w; t /= g.tiles_w;
+        const int th = t % g.tiles_h; t /= g.tiles_h;
+        const int tn = t % g.tiles_n; t /= g.tiles_n;
+        const int n0 = t * N_TILE;
+        const int x0 = tw * g.TW * g.stride - g.pad, y0 = th * g.TH * g.stride - g.pad, img0 = tn * g.TN;
+        for (int i = 0; i < n_it; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          const int q0 = i * g.group;
+          const int cnt = min(g.group, n_sub - q0);
+          mbar_expect_tx(&full_bar[s], (uint32_t)cnt * (a_sub_bytes + b_sub_bytes));
+          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+          for (int j = 0; j < cnt; ++j) {
+            const int q = q0 + j;
+            const int tap = q / g.nchunk, ch = (q - tap * g.nchunk) * g.bc;
+            const int ky = tap / g.kw, kx = tap - ky * g.kw;
+            tma_load_4d(&tmx, &full_bar[s], a_base + j * (128 * bcb), ch, x0 + kx, y0 + ky, img0);
+            const int wtap = g.flip ? taps - 1 - tap : tap;
+            if (!B_MN) {           // rows = output channels, columns = (tap, input channel): K-major B
+              tma_load_2d(&tmw, &full_bar[s], b_base + j * b_sub_bytes, wtap * g.cin + ch, n0);
+            } else {               // rows = reduction channels, columns = (tap, output channel): MN-major B, <= 64 columns per box
+              constexpr int NA = N_TILE < 64 ? N_TILE : 64;
+#pragma unroll
+              for (int a = 0; a < N_TILE / NA; ++a)
+                tma_load_2d(&tmw, &full_bar[s], b_base + j * b_sub_bytes + a * (g.bc * NA * 2), wtap * g.cout + n0 + a * NA, ch);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer ------------------------------------------------
+    const uint32_t idesc = make_idesc(TC_M, N_TILE, 0, B_MN ? 1 : 0);
+    const uint32_t a_layout = umma_layout_of(bcb);
+    uint32_t it = 0, tcount = 0;
+    for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++tcount) {
+      const uint32_t as = tcount & 1;
+      mbar_wait(&tempty_bar[as], ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * N_TILE;
+      for (int i = 0; i < n_it; ++i, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+          const int cnt = min(g.group, n_sub - i * g.group);
+          for (int j = 0; j < cnt; ++j) {
+            const uint32_t a_sub = a_base + j * (128 * bcb), b_sub = b_base + j * b_sub_bytes;
+            for (int kk = 0; kk < g.bc / 16; ++kk) {
+              const uint64_t ad = make_desc_sw(a_sub + kk * 32, 16, 8 * bcb, a_layout);
+              uint64_t bd;
+              if (!B_MN) {
+                bd = make_desc_sw(b_sub + kk * 32, 16, 8 * bcb, a_layout);
+              } else {
+                constexpr int NAB = (N_TILE < 64 ? N_TILE : 64) * 2;     // bytes per MN-major row (one atom of columns)
+                bd = make_desc_sw(b_sub + kk * 16 * NAB, g.bc * NAB, 8 * NAB, umma_layout_of(NAB));
+              }
+              umma_bf16(tacc, ad, bd, idesc, (i > 0 || j > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);                          // stage reusable once these MMAs have read it
+          if (i == n_it - 1) umma_commit(&tfull_bar[as]);      // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ------------------------------------------------ epilogue ------------------------------------------------
+    const int et = threadIdx.x - 64;                           // 0..127
+    const int quad = warp & 3;                                 // TMEM lane quadrant this warp may read
+    const int m = quad * 32 + lane;                            // tile row = TMEM lane
+    uint32_t tcount = 0, cb = 0;
+    for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++tcount) {
+      int t = work;
+      const int tw = t % g.tiles_w; t /= g.tiles_w;
+      const int th = t % g.tiles_h; t /= g.tiles_h;
+      const int tn = t % g.tiles_n; t /= g.tiles_n;
+      const int n0 = t * N_TILE;
+      const int ow0 = tw * g.TW, oh0 = th * g.TH, img0 = tn * g.TN;
+      // this thread's output pixel
+      const int mi = m / (g.TH * g.TW), mr = m - mi * (g.TH * g.TW);
+      const int mh = mr / g.TW, mw = mr - mh * g.TW;
+      const bool valid = m < rows_box && img0 + mi < g.N && oh0 + mh < g.Ho && ow0 + mw < g.Wo;
+      const long long pix = ((long long)(img0 + mi) * g.Ho + (oh0 + mh)) * g.Wo + (ow0 + mw);
+      const uint32_t as = tcount & 1;
+      mbar_wait(&tfull_bar[as], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + as * N_TILE;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += CB_COLS, cb ^= 1) {
+        if (et == 0) tma_store_wait_read<1>();                 // the store issued from this buffer two chunks ago has read it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* crow = cbuf + cb * CB_BYTES;
+#pragma unroll 1
+        for (int c1 = 0; c1 < CB_COLS; c1 += 32) {
+          constexpr int W32 = CB_COLS < 32 ? CB_COLS : 32;     // columns handled per TMEM load (16 or 32)
+          uint32_t v[32];
+          if (W32 == 32) {
+            tmem_ld32(tacc + (uint32_t)(c0 + c1), v);
+          } else {
+            tmem_ld16(tacc + (uint32_t)(c0 + c1), v);
+          }
+          if (c0 + CB_COLS >= N_TILE && c1 + 32 >= CB_COLS) {  // last read of this accumulator stage
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[as]);
+          }
+#pragma unroll
+          for (int q = 0; q < W32 / 8; ++q) {
+            const int c = n0 + c0 + c1 + 8 * q;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * q + e]);
+            if (bias != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (res != nullptr && valid) {
+              const uint4 r = *reinterpret_cast<const uint4*>(res + pix * g.cout + c);
+              const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 rf = __bfloat1622float2(rp[e]);
+                f[2 * e] += rf.x;
+                f[2 * e + 1] += rf.y;
+              }
+            }
+            if (g.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16(__float_as_uint(f[0]), __float_as_uint(f[1]));
+            o.y = pack_bf16(__float_as_uint(f[2]), __float_as_uint(f[3]));
+            o.z = pack_bf16(__float_as_uint(f[4]), __float_as_uint(f[5]));
+            o.w = pack_bf16(__float_as_uint(f[6]), __float_as_uint(f[7]));
+            const uint32_t off = swz((uint32_t)(m * CB_ROW_BYTES + (c1 + 8 * q) * 2), CB_MASK);
+            *reinterpret_cast<uint4*>(crow + off) = o;
+          }
+        }
+        fence_proxy_async();                                   // generic-proxy writes -> visible to the TMA store
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          tma_store_4d(&tmy, smem_u32(crow), n0 + c0, ow0, oh0, img0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (et == 0) tma_store_wait<0>();                          // global writes complete before the kernel ends
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// pick the output-tile extent (TW x TH x TN <= 128 pixels) that wastes the fewest MMA rows over the whole output
+void choose_tile(int Wo, int Ho, int N, int* TW, int* TH, int* TN) {
+  double best = -1.0;
+  *TW = *TH = *TN = 1;
+  for (int tw = 1; tw <= Wo && tw <= 128; ++tw) {
+    for (int th = 1; th <= Ho && tw * th <= 128; ++th) {
+      int tn = 1;
+      if (tw == Wo && th == Ho) tn = 128 / (tw * th) < N ? 128 / (tw * th) : N;
+      const long long tiles = (long long)esb_div_up(Wo, tw) * esb_div_up(Ho, th) * esb_div_up(N, tn);
+      const double eff = (double)Wo * Ho * N / ((double)tiles * 128.0) + 1e-6 * tw;   // ties: longer contiguous rows
+      if (eff > best) { best = eff; *TW = tw; *TH = th; *TN = tn; }
+    }
+  }
+}
+
+template <int N_TILE, bool B_MN>
+int launch(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tmy, const float* bias, const void* res,
+           ConvGeom g, cudaStream_t stream) {
+  constexpr int CB_COLS = N_TILE < 64 ? N_TILE : 64;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + N_TILE * 128;
+  const int n_it = (g.kh * g.kw * g.nchunk + g.group - 1) / g.group;
+  (void)n_it;
+  // the stage ring runs ahead ACROSS output tiles (persistent CTA), so its depth is set by shared memory, not by the filter:
+  // two CTAs per SM up to N_TILE = 64 (~100 KB each), one CTA per SM above
+  const int budget = (N_TILE <= 64 ? 100 : 200) * 1024 - 2 * 128 * CB_COLS * 2;
+  int stages = budget / STAGE_BYTES;
+  stages = stages > 6 ? 6 : stages < 2 ? 2 : stages;
+  g.stages = stages;
+  const size_t smem = (size_t)stages * STAGE_BYTES + 2 * 128 * CB_COLS * 2 + (2 * stages + 4) * 8 + 16 + 1024;
+  auto kern = conv_tma_kernel<N_TILE, B_MN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { esb_set_error("conv_tma: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return ESB_ECUDA; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_work = (long long)g.tiles_w * g.tiles_h * g.tiles_n * g.n_blocks;
+  const int per_sm = (smem <= 110 * 1024 && 2 * N_TILE * 2 <= 512) ? 2 : 1;
+  long long grid = (long long)sms * per_sm;
+  if (grid > n_work) grid = n_work;
+  kern<<<(unsigned)grid, THREADS, smem, stream>>>(tmx, tmw, tmy, bias, (const __nv_bfloat16*)res, g);
+  return ESB_OK;
+}
+
+// in (N, Hi, Wi, Ci) -> out (N, Ho, Wo, Co); w_rows x w_cols is the filter matrix as stored (OHWI: Co rows, kh*kw*Ci columns)
+int conv_tma_run(const void* in, const void* w, const float* bias, const void* res, void* out, int N, int Hi, int Wi, int Ci,
+                 int Ho, int Wo, int Co, int kh, int kw, int stride, int pad, int relu, bool dgrad, cudaStream_t stream) {
+  ConvGeom g{};
+  g.Wo = Wo; g.Ho = Ho; g.N = N;
+  g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad;
+  g.cin = Ci; g.cout = Co; g.relu = relu; g.flip = dgrad ? 1 : 0;
+  g.bc = Ci >= 64 ? 64 : Ci;
+  g.nchunk = Ci / g.bc;
+  g.group = 64 / g.bc;
+  choose_tile(Wo, Ho, N, &g.TW, &g.TH, &g.TN);
+  g.tiles_w = esb_div_up(Wo, g.TW); g.tiles_h = esb_div_up(Ho, g.TH); g.tiles_n = esb_div_up(N, g.TN);
+  const int n_tile = Co >= 256 ? 256 : Co;
+  g.n_blocks = Co / n_tile;
+  CUtensorMap tmx, tmw, tmy;
+  {   // activations: {C, W, H, N}, box {bc, span_w, span_h, TN}, element strides {1, s, s, 1}
+    unsigned long long dims[4] = {(unsigned long long)Ci, (unsigned long long)Wi, (unsigned long long)Hi, (unsigned long long)N};
+    unsigned long long str[3] = {(unsigned long long)Ci * 2, (unsigned long long)Wi * Ci * 2, (unsigned long long)Hi * Wi * Ci * 2};
+    unsigned box[4] = {(unsigned)g.bc, (unsigned)((g.TW - 1) * stride + 1), (unsigned)((g.TH - 1) * stride + 1), (unsigned)g.TN};
+    unsigned es[4] = {1, (unsigned)stride, (unsigned)stride, 1};
+    int rc = esb_tma_encode(&tmx, in, 4, dims, str, box, es, g.bc * 2 >= 128 ? 128 : g.bc * 2);
+    if (rc != ESB_OK) return rc;
+  }
+  const int taps = kh * kw;
+  if (!dgrad) {   // OHWI (Co, taps*Ci): box {bc, n_tile}
+    unsigned long long dims[2] = {(unsigned long long)taps * Ci, (unsigned long long)Co};
+    unsigned long long str[1] = {(unsigned long long)taps * Ci * 2};
+    unsigned box[2] = {(unsigned)g.bc, (unsigned)n_tile};
+    int rc = esb_tma_encode(&tmw, w, 2, dims, str, box, nullptr, g.bc * 2 >= 128 ? 128 : g.bc * 2);
+    if (rc != ESB_OK) return rc;
+  } else {        // the forward filter OHWI (Ci_fwd = Co here ... ) read as MN-major B: rows = reduction channel (Ci of this GEMM)
+    const int na = n_tile < 64 ? n_tile : 64;
+    unsigned long long dims[2] = {(unsigned long long)taps * Co, (unsigned long long)Ci};
+    unsigned long long str[1] = {(unsigned long long)taps * Co * 2};
+    unsigned box[2] = {(unsigned)na, (unsigned)g.bc};
+    int rc = esb_tma_encode(&tmw, w, 2, dims, str, box, nullptr, na * 2);
+    if (rc != ESB_OK) return rc;
+  }
+  {   // output store: {Co, Wo, Ho, N}, box {<=64 channels, TW, TH, TN}
+    const int cb = n_tile < 64 ? n_tile : 64;
+    unsigned long long dims[4] = {(unsigned long long)Co, (unsigned long long)Wo, (unsigned long long)Ho, (unsigned long long)N};
+    unsigned long long str[3] = {(unsigned long long)Co * 2, (unsigned long long)Wo * Co * 2, (unsigned long long)Ho * Wo * Co * 2};
+    unsigned box[4] = {(unsigned)cb, (unsigned)g.TW, (unsigned)g.TH, (unsigned)g.TN};
+    int rc = esb_tma_encode(&tmy, out, 4, dims, str, box, nullptr, cb * 2);
+    if (rc != ESB_OK) return rc;
+  }
+  int rc;
+#define ESB_CT(NT)                                                                       \
+  (dgrad ? launch<NT, true>(tmx, tmw, tmy, bias, res, g, stream) : launch<NT, false>(tmx, tmw, tmy, bias, res, g, stream))
+  switch (n_tile) {
+    case 16: rc = ESB_CT(16); break;
+    case 32: rc = ESB_CT(32); break;
+    case 64: rc = ESB_CT(64); break;
+    case 128: rc = ESB_CT(128); break;
+    case 256: rc = ESB_CT(256); break;
+    default: esb_set_error("conv_tma: unsupported output channel count %d (16, 32, 64, 128 or a multiple of 256)", Co); return ESB_EINVAL;
+  }
+#undef ESB_CT
+  if (rc != ESB_OK) return rc;
+  ESB_CUDA_LAUNCH_CHECK("conv_tma_kernel");
+  return ESB_OK;
+}
+
+bool channels_ok(int c) { return c == 16 || c == 32 || (c >= 64 && c % 64 == 0); }
+
+}  // namespace
+
+// y (n,Ho,Wo,cout) = act(conv(x (n,H,W,cin), w_ohwi (cout,kh,kw,cin)) + bias + residual), NHWC bf16, fp32 accumulate.
+// bias fp32 (cout) or NULL; residual bf16 (n,Ho,Wo,cout) or NULL. cin, cout in {16, 32, 64k}; cout <= 256 or a multiple of 256.
+extern "C" int esb_conv2d_tma_fwd(const void* x, const void* w_ohwi, const float* bias, const void* residual, void* y,
+                                  int n_img, int H, int W, int cin, int cout, int kh, int kw, int stride, int pad, int relu,
+                                  void* stream_) {
+  ESB_CHECK_ARG(channels_ok(cin) && channels_ok(cout), "esb_conv2d_tma_fwd: channels must be 16, 32 or a multiple of 64");
+  ESB_CHECK_ARG(cout <= 256 || cout % 256 == 0, "esb_conv2d_tma_fwd: Cout above 256 must be a multiple of 256");
+  ESB_CHECK_ARG(cout <= 256 ? (cout & (cout - 1)) == 0 : true, "esb_conv2d_tma_fwd: Cout <= 256 must be a power of two");
+  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && stride >= 1 && stride <= 8 && pad >= 0, "esb_conv2d_tma_fwd: bad filter geometry");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tma_fwd: empty output");
+  if (n_img == 0) return ESB_OK;
+  return conv_tma_run(x, w_ohwi, bias, residual, y, n_img, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, relu, false,
+                      (cudaStream_t)stream_);
+}
+
+// Input gradient of a STRIDE-1 convolution: dx (n,H,W,cin) from dy (n,Ho,Wo,cout) and the forward filter w_ohwi as stored
+// (taps visited in reverse, filter read as the MN-major B operand).
+extern "C" int esb_conv2d_tma_dgrad(const void* dy, const void* w_ohwi, void* dx, int n_img, int H, int W, int cin, int cout,
+                                    int kh, int kw, int pad, void* stream_) {
+  ESB_CHECK_ARG(channels_ok(cin) && channels_ok(cout), "esb_conv2d_tma_dgrad: channels must be 16, 32 or a multiple of 64");
+  ESB_CHECK_ARG(cin <= 256 ? (cin & (cin - 1)) == 0 : cin % 256 == 0, "esb_conv2d_tma_dgrad: Cin must be a power of two <= 256 or a multiple of 256");
+  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && pad >= 0 && pad < kh && pad < kw, "esb_conv2d_tma_dgrad: bad filter geometry");
+  const int Ho = H + 2 * pad - kh + 1, Wo = W + 2 * pad - kw + 1;
+  ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tma_dgrad: empty output");
+  if (n_img == 0) return ESB_OK;
+  // dx = conv(dy, flipped filter) with padding kh-1-pad; reduction channels = cout, output channels = cin
+  return conv_tma_run(dy, w_ohwi, nullptr, nullptr, dx, n_img, Ho, Wo, cout, H, W, cin, kh, kw, 1, kh - 1 - pad, 0, true,
+                      (cudaStream_t)stream_);
+}

@@ -102,6 +102,32 @@ int esb_conv2d_tc_dgrad(const void* dy, const void* w_ihwo, void* dx, int n_img,
  * zeroed by the caller, row r = (ky,kx,ci): dW[co,ci,ky,kx] = dw_t[(ky*kw+kx)*cin+ci, co]. */
 int esb_conv2d_tc_wgrad(const void* x, const void* dy, float* dw_t, int n_img, int H, int W, int cin, int cout, int kh,
                         int kw, int stride, int pad, void* stream);
+/* The per-view 2D backbone's convolution as a persistent TMA + tcgen05 implicit GEMM (csrc/conv_tma.cu): activations,
+ * filter and output move with cp.async.bulk.tensor tiles (zero padding = TMA out-of-bounds fill, stride = tensor-map element
+ * strides), accumulators live in TMEM, bias + residual + ReLU are fused into the epilogue. Replaces the cuDNN call behind
+ * mmdet.ResNet (embodiedscan/models/detectors/sparse_featfusion_single_stage.py:130-136). x (n_img,H,W,cin) bf16 NHWC;
+ * w_ohwi (cout,kh,kw,cin) bf16; bias (cout) fp32 or NULL; residual / y (n_img,Ho,Wo,cout) bf16 NHWC, residual may be NULL.
+ * cin, cout in {16, 32, 64, 128, 256, 512, ...}. */
+int esb_conv2d_tma_fwd(const void* x, const void* w_ohwi, const float* bias, const void* residual, void* y, int n_img,
+                       int H, int W, int cin, int cout, int kh, int kw, int stride, int pad, int relu, void* stream);
+/* Input gradient of a stride-1 convolution with the same kernel: dx (n_img,H,W,cin) from dy (n_img,Ho,Wo,cout) and the
+ * forward filter as stored (taps visited in reverse, filter read as the MN-major B operand: no transposed copy). */
+int esb_conv2d_tma_dgrad(const void* dy, const void* w_ohwi, void* dx, int n_img, int H, int W, int cin, int cout, int kh,
+                         int kw, int pad, void* stream);
+/* Direct (SIMT, fp32-accumulate) NHWC convolution and its gradients (csrc/conv2d_direct.cu): the fp32 parity arithmetic of
+ * every 2D convolution of the image backbone, and the 7x7/2 stem on the 3-channel image in either dtype. x (n_img,H,W,cin),
+ * w_ohwi (cout,kh,kw,cin), y / residual (n_img,Ho,Wo,cout) in `dtype` (ESB_F32 / ESB_BF16); bias fp32 or NULL. */
+int esb_conv2d_direct_fwd(const void* x, const void* w_ohwi, const float* bias, const void* residual, void* y, int n_img,
+                          int H, int W, int cin, int cout, int kh, int kw, int stride, int pad, int relu, int dtype,
+                          void* stream);
+int esb_conv2d_direct_dgrad(const void* dy, const void* w_ohwi, void* dx, int n_img, int H, int W, int cin, int cout, int kh,
+                            int kw, int stride, int pad, int dtype, void* stream);
+/* dw_ohwi (cout,kh,kw,cin) fp32, zeroed by the caller (pixel slices accumulate through fp32 atomics) */
+int esb_conv2d_direct_wgrad(const void* x, const void* dy, float* dw_ohwi, int n_img, int H, int W, int cin, int cout, int kh,
+                            int kw, int stride, int pad, int dtype, void* stream);
+/* k x k / stride / pad max pooling on NHWC (the stem's F.max_pool2d(3, 2, 1)); forward only (the stem is frozen) */
+int esb_maxpool2d_nhwc(const void* x, void* y, int n_img, int H, int W, int C, int k, int stride, int pad, int dtype,
+                       void* stream);
 
 /* ---- point painting (batch_point_sample + apply_3d_transformation + batch_points_cam2img + F.grid_sample;
  * embodiedscan/models/layers/fusion_layers/point_fusion.py:208-311, structures/bbox_3d/utils.py:289-332) -------- */
