@@ -320,22 +320,35 @@ conv2d_tc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
     fence_proxy_async();
     for (int d = (total > LAG ? total - LAG : 0); d < total; ++d) mbar_arrive(&full_bar[d % STAGES]);
 
-    // epilogue: TMEM lane = reduction element r (within the 128 slice), column = co
+    // epilogue: TMEM lane = reduction element r (within the 128 slice), column = co; transposed through the idle stage
+    // buffers so a warp adds contiguous runs of one dW^T row with 16-byte vector atomics (see spconv_tc_wgrad_kernel)
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int rr = r0 + threadIdx.x;
-    float* dwrow = dw + (long long)rr * cout + co0;
+    constexpr int PITCH = N_TILE + 4;
+    float* stg = reinterpret_cast<float*>(smem);
 #pragma unroll 1
     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      if (rr < R) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (co0 + c0 + i < cout) atomicAdd(dwrow + c0 + i, __uint_as_float(v[i]));
-      }
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stg + threadIdx.x * PITCH + c0 + 4 * q) =
+            make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                        __uint_as_float(v[4 * q + 3]));
     }
     tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int lane = threadIdx.x & 31;
+    for (int i = 0; i < 32; ++i) {
+      const int rl = warp * 32 + i;
+      const int rr = r0 + rl;
+      if (rr >= R) break;
+      float* dwrow = dw + (long long)rr * cout + co0;
+#pragma unroll
+      for (int c = lane * 4; c < N_TILE; c += 128)
+        if (co0 + c < cout)                              // cout % 8 == 0: a float4 is all in or all out
+          atomicAdd(reinterpret_cast<float4*>(dwrow + c), *reinterpret_cast<const float4*>(stg + rl * PITCH + c));
+    }
   } else {
     const uint32_t idesc = make_idesc(128, N_TILE, 1, 1);
     for (int it = 0; it < total; ++it) {

@@ -316,21 +316,35 @@ spconv_tc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
     fence_proxy_async();
     for (int d = (total > LAG ? total - LAG : 0); d < total; ++d) mbar_arrive(&full_bar[d % STAGES]);
 
-    // epilogue: TMEM lane = ci (within the 128 slice), column = co
+    // epilogue: TMEM lane = ci (within the 128 slice), column = co. The tile is transposed through the (now idle) stage
+    // buffers so that a warp adds whole 512-byte runs of one dW row with 16-byte vector atomics (coalesced RED traffic);
+    // the round-1 epilogue issued 32 scalar atomics per thread with a lane stride of one row.
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int ci = ci0 + threadIdx.x;
-    float* dwrow = dw + ((long long)k * cin + ci) * cout + co0;
+    constexpr int PITCH = N_TILE + 4;                 // floats; +4 keeps the per-lane float4 stores conflict-free
+    float* stg = reinterpret_cast<float*>(smem);
 #pragma unroll 1
     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      if (ci < cin) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(dwrow + c0 + i, __uint_as_float(v[i]));
-      }
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stg + threadIdx.x * PITCH + c0 + 4 * q) =
+            make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                        __uint_as_float(v[4 * q + 3]));
     }
     tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int lane = threadIdx.x & 31;
+    for (int rr = 0; rr < 32; ++rr) {
+      const int r = warp * 32 + rr;
+      const int ci = ci0 + r;
+      if (ci >= cin) break;
+      float* dwrow = dw + ((long long)k * cin + ci) * cout + co0;
+#pragma unroll
+      for (int c = lane * 4; c < N_TILE; c += 128)
+        atomicAdd(reinterpret_cast<float4*>(dwrow + c), *reinterpret_cast<const float4*>(stg + r * PITCH + c));
+    }
   } else {
     const uint32_t idesc = make_idesc(128, N_TILE, 1, 1);
     for (int it = 0; it < total; ++it) {

@@ -339,11 +339,21 @@ class FCAF3DHeadRotMat(nn.Module):
     def _forward_single_level(self, x: SP.SparseTensor, scale: Scale, need_prune_score: bool = True):
         """_forward_single (fcaf3d_head.py:1116-1149) on whole-batch rows; the three 1x1 heads are two GEMMs."""
         f = x.F
-        w_small = torch.cat([self.conv_center.kernel, self.conv_reg.kernel], 1).to(f.dtype)
-        small = (f @ w_small).float()
+        if f.is_cuda and f.dtype == torch.bfloat16 and f.shape[1] % 64 == 0:
+            # ONE tensor-core GEMM for the three heads: [cls | centre | reg | zero pad] widened to a multiple of 64 columns
+            n_cls, n_reg = self.conv_cls.kernel.shape[1], self.conv_reg.kernel.shape[1]
+            width = (n_cls + 1 + n_reg + 63) // 64 * 64
+            w_all = torch.cat([self.conv_cls.kernel, self.conv_center.kernel, self.conv_reg.kernel,
+                               self.conv_cls.kernel.new_zeros(f.shape[1], width - n_cls - 1 - n_reg)], 1).to(f.dtype)
+            out = SP.rows_gemm(f, w_all)
+            cls_pred = out[:, :n_cls] + self.conv_cls.bias.to(f.dtype)
+            small = out[:, n_cls:n_cls + 1 + n_reg].float()
+        else:
+            w_small = torch.cat([self.conv_center.kernel, self.conv_reg.kernel], 1).to(f.dtype)
+            small = (f @ w_small).float()
+            cls_pred = torch.addmm(self.conv_cls.bias.to(f.dtype), f, self.conv_cls.kernel.to(f.dtype))
         center_pred = small[:, :1]
         reg_final = small[:, 1:]
-        cls_pred = torch.addmm(self.conv_cls.bias.to(f.dtype), f, self.conv_cls.kernel.to(f.dtype))
         prune_scores = x.replace_feature(cls_pred.max(dim=1, keepdim=True).values.float()) if need_prune_score else None
         reg_distance = torch.exp(scale(reg_final[:, :6])).clamp(min=1e-3)
         bbox_pred = torch.cat((reg_distance, reg_final[:, 6:]), dim=1)

@@ -69,6 +69,8 @@ class FlatArena:
         """fp32 master arena -> bf16 compute copy: ONE launch for the whole model."""
         if self.bf16 is not None:
             call('esb_cast_f32_to_bf16', ptr(self.flat), ptr(self.bf16), self.numel, stream())
+            for p in self.params:            # consumers use the shadow only while the parameter is unchanged since now
+                p._esb_bf16_version = p._version
 
     def zero_grad(self):
         self.grad.zero_()

@@ -274,9 +274,8 @@ class _SparseConv(torch.autograd.Function):
     def forward(ctx, x, weight, kmap: KernelMap, cin, cout):
         K = kmap.K
         x = x.contiguous()
-        w = getattr(weight, '_esb_bf16', None) if x.dtype == torch.bfloat16 else None   # arena shadow copy (engine.py)
-        if w is None:
-            w = weight.detach().to(x.dtype).contiguous()
+        # bf16: the arena's shadow copy when it mirrors the current value (engine.py), else a fresh cast
+        w = bf16_operand(weight) if x.dtype == torch.bfloat16 else weight.detach().to(x.dtype).contiguous()
         y = torch.empty((kmap.n_out, cout), dtype=x.dtype, device=x.device)
         tc = USE_TENSOR_CORES and x.dtype == torch.bfloat16 and cin % 64 == 0 and cout % 64 == 0
         if tc:   # the stored (K,cin,cout) kernel is the MN-major B operand: no transpose copy
@@ -325,6 +324,98 @@ class _SparseConv(torch.autograd.Function):
             else:
                 dw = dw.view(ctx.wshape)
         return dx, dw, None, None, None
+
+
+class _ShadowCast(torch.autograd.Function):
+    """fp32 parameter -> its bf16 operand copy (the arena's shadow when it is fresh, else a cast), connected to autograd."""
+
+    @staticmethod
+    def forward(ctx, p):
+        return bf16_operand(p)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.float()
+
+
+def bf16_operand(p: torch.Tensor) -> torch.Tensor:
+    """The bf16 copy of a parameter that kernels read: the arena shadow if it mirrors the CURRENT value (engine.FlatArena
+    stamps the parameter version at every refresh; load_state_dict / init / manual edits bump it), else a fresh cast."""
+    sh = getattr(p, '_esb_bf16', None)
+    if sh is not None and getattr(p, '_esb_bf16_version', None) == p._version:
+        return sh
+    return p.detach().to(torch.bfloat16).contiguous()
+
+
+_IDENTITY_MAPS = {}
+
+
+def _identity_map(n: int, device):
+    """Kernel map of a dense rows GEMM: ONE offset whose neighbour of row i is row i (cached per row count)."""
+    key = (n, str(device))
+    m = _IDENTITY_MAPS.get(key)
+    if m is None:
+        if len(_IDENTITY_MAPS) > 64:
+            _IDENTITY_MAPS.clear()
+        ar = torch.arange(n, dtype=torch.int32, device=device)
+        masks = torch.ones(max((n + 127) // 128, 1), dtype=torch.int32, device=device)
+        koff = torch.tensor([0, n], dtype=torch.int32, device=device)
+        m = _IDENTITY_MAPS[key] = (ar, masks, koff)
+    return m
+
+
+class _RowsGemmTC(torch.autograd.Function):
+    """y (N, cout) = x (N, cin) @ w (cin, cout) in bf16 on the sparse-conv tensor-core kernels with the identity map:
+    forward = spconv_tc_fwd (w as the MN-major B operand), dx = the same kernel with w read K-major, dw = spconv_tc_wgrad
+    over the identity pair list. The dense contractions of the head (generative transpose, 1x1 convolutions;
+    embodiedscan/models/dense_heads/fcaf3d_head.py:937-941,970-982) stay on the library's own kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x = x.contiguous()
+        w = w.contiguous()
+        N, cin = x.shape
+        cout = w.shape[1]
+        y = torch.empty((N, cout), dtype=torch.bfloat16, device=x.device)
+        ar, masks, koff = _identity_map(N, x.device)
+        if N:
+            call('esb_spconv_tc_fwd', ptr(x), ptr(w), ptr(ar), ptr(masks), ptr(y), N, cin, cout, 1, 1, stream())
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        N, cin = x.shape
+        cout = w.shape[1]
+        dy = dy.contiguous()
+        ar, masks, koff = _identity_map(N, x.device)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if N:
+                call('esb_spconv_tc_fwd', ptr(dy), ptr(w), ptr(ar), ptr(masks), ptr(dx), N, cout, cin, 1, 0, stream())
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros((cin, cout), dtype=torch.float32, device=x.device)
+            if N:
+                call('esb_spconv_tc_wgrad', ptr(x), ptr(dy), ptr(ar), ptr(ar), ptr(koff), ptr(dw), N, cin, cout, 1, stream())
+        return dx, dw
+
+
+def rows_gemm(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """x (N, cin) @ w (cin, cout). bf16 CUDA rows with channel counts that tile (multiples of 64) run on the library's
+    tensor-core kernels; anything else (fp32 parity arithmetic, odd widths) is a plain matmul."""
+    if (USE_TENSOR_CORES and x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.shape[1] % 64 == 0
+            and w.shape[1] % 64 == 0):
+        return _RowsGemmTC.apply(x, w)
+    return x @ w.to(x.dtype)
+
+
+def weight_operand(p: torch.Tensor, dtype) -> torch.Tensor:
+    """A parameter as the operand of compute dtype `dtype`, connected to autograd."""
+    if dtype == torch.bfloat16 and p.is_cuda and p.dtype == torch.float32:
+        return _ShadowCast.apply(p)
+    return p.to(dtype)
 
 
 class _MaxPool(torch.autograd.Function):
@@ -630,7 +721,7 @@ class MinkowskiConvolution(nn.Module):
         mgr = x.coordinate_manager
         in_key = x.coordinate_map_key
         if self.kernel_size == 1 and self.stride == 1:
-            y = x.F @ self.kernel.to(x.F.dtype)   # plain dense GEMM over rows
+            y = rows_gemm(x.F, weight_operand(self.kernel, x.F.dtype))   # dense GEMM over rows, identity kernel map
             out_key = in_key
         else:
             out_key = mgr.stride_key(in_key, self.stride) if self.stride > 1 else in_key
@@ -656,8 +747,8 @@ class MinkowskiGenerativeConvolutionTranspose(nn.Module):
     def forward(self, x: SparseTensor) -> SparseTensor:
         mgr = x.coordinate_manager
         out_key = mgr.generative_key(x.coordinate_map_key)
-        w = self.kernel.to(x.F.dtype).permute(1, 0, 2).reshape(self.in_channels, 8 * self.out_channels)
-        y = (x.F @ w).view(-1, self.out_channels)
+        w = weight_operand(self.kernel, x.F.dtype).permute(1, 0, 2).reshape(self.in_channels, 8 * self.out_channels)
+        y = rows_gemm(x.F, w).view(-1, self.out_channels)
         return SparseTensor(y, coordinate_map_key=out_key, coordinate_manager=mgr)
 
 
