@@ -430,6 +430,25 @@ class _BasicBlock2D(nn.Module):
         return self.cb2(self.cb1(x, True), True, res=idt)
 
 
+class _GraphShim(nn.Module):
+    """What torch.cuda.make_graphed_callables needs of a module (parameters, buffers, training flag, a patchable forward)
+    for ONE input shape of a ResNet, without registering the net as a child (no reference cycle in the module tree)."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.__dict__['_net'] = net
+        self.training = net.training
+
+    def parameters(self, recurse=True):
+        return self.__dict__['_net'].parameters(recurse)
+
+    def buffers(self, recurse=True):
+        return self.__dict__['_net'].buffers(recurse)
+
+    def forward(self, x):
+        return self.__dict__['_net']._forward_impl(x)
+
+
 # state_dict names follow mmdet/torchvision: conv1/bn1, layer{i}.{j}.conv{k}/bn{k}, downsample.0/.1
 _RENAME = {'cb1.conv': 'conv1', 'cb1.bn': 'bn1', 'cb2.conv': 'conv2', 'cb2.bn': 'bn2', 'cb3.conv': 'conv3',
            'cb3.bn': 'bn3', 'ds.conv': 'downsample.0', 'ds.bn': 'downsample.1', 'stem.conv': 'conv1', 'stem.bn': 'bn1'}
@@ -495,6 +514,11 @@ class ResNet(nn.Module):
         return self
 
     def forward(self, x):
+        if self._graphable(x):
+            return self._graphed_forward(x)
+        return self._forward_impl(x)
+
+    def _forward_impl(self, x):
         x = self.stem(x, True)
         x = maxpool2d(x, 3, 2, 1)
         outs = []
@@ -503,6 +527,35 @@ class ResNet(nn.Module):
             if i in self.out_indices:
                 outs.append(x)
         return tuple(outs)
+
+    # ---- CUDA graphs: the image branch has static shapes (views x H x W), so its ~60 forward launches and ~150 backward
+    # launches replay as TWO graph launches per step; the host thread is free for the data-dependent 3D plan.
+    def _graphable(self, x):
+        import os
+        return (x.is_cuda and self.training and torch.is_grad_enabled() and x.dtype == torch.bfloat16
+                and conv2d_backend() == 'own' and os.environ.get('ESB200_GRAPH2D', '1') != '0'
+                and not torch.cuda.is_current_stream_capturing()
+                and all(not b.training for b in self.modules() if isinstance(b, nn.BatchNorm2d))
+                and any(p.requires_grad for p in self.parameters()))
+
+    def _graph_signature(self):
+        # frozen tensors are baked into the captured constants (folded filters): any in-place change invalidates the graph
+        return tuple(t._version for t in self.buffers()) + tuple(p._version for p in self.parameters() if not p.requires_grad) \
+            + tuple(p.data_ptr() for p in self.parameters() if p.requires_grad)
+
+    def _graphed_forward(self, x):
+        graphs = self.__dict__.setdefault('_graphs', {})
+        key = (tuple(x.shape), x.device.index)
+        sig = self._graph_signature()
+        entry = graphs.get(key)
+        if entry is None or entry[0] != sig:
+            if len(graphs) >= 4:
+                graphs.clear()
+            shim = _GraphShim(self)
+            sample = torch.empty_like(x).copy_(x)
+            fn = torch.cuda.make_graphed_callables(shim, (sample, ), num_warmup_iters=3, allow_unused_input=True)
+            entry = graphs[key] = (sig, fn)
+        return entry[1](x)
 
     # checkpoint compatibility with mmdet / torchvision parameter names: a state-dict hook (not a `state_dict` override,
     # which nn.Module ignores for nested modules) so `detector.state_dict()` carries `backbone.layer1.0.conv1.weight`

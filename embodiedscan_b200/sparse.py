@@ -41,7 +41,7 @@ def _timed_conv_call(kind, kmap, cin, cout, dtype, *args):
     call(*args)
     e1.record()
     # keep only the tiny (K+1) pair-offset tensor: holding the KernelMap would pin hundreds of MB of maps per step
-    CONV_PROFILE['records'].append((kind, kmap.pairs[2], kmap.K, cin, cout, dtype, e0, e1))
+    CONV_PROFILE['records'].append((kind, kmap.pairs[2], kmap.K, cin, cout, dtype, e0, e1, kmap.n_in, kmap.n_out))
 
 
 def _count_use(*params):
