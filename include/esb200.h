@@ -102,6 +102,15 @@ int esb_conv2d_tc_dgrad(const void* dy, const void* w_ihwo, void* dx, int n_img,
  * zeroed by the caller, row r = (ky,kx,ci): dW[co,ci,ky,kx] = dw_t[(ky*kw+kx)*cin+ci, co]. */
 int esb_conv2d_tc_wgrad(const void* x, const void* dy, float* dw_t, int n_img, int H, int W, int cin, int cout, int kh,
                         int kw, int stride, int pad, void* stream);
+/* TMA-fed variants of the two tensor-core sparse-conv entry points (csrc/spconv_tma.cu): gathered rows arrive through
+ * cp.async.bulk.tensor tile::gather4 (missing neighbours = out-of-bounds rows = zeros), filter tiles through tiled TMA boxes,
+ * forward/dgrad CTAs own 256 output rows per filter stage when the grid allows. Same arguments as esb_spconv_tc_fwd /
+ * esb_spconv_tc_wgrad plus the row counts of the gathered tensors (the extents of their tensor maps). */
+int esb_spconv_tma_fwd(const void* x, const void* w, const int* nbr, const unsigned* masks, void* y, long long n_in,
+                       long long n_out, int cin, int cout, int K, int w_layout, void* stream);
+int esb_spconv_tma_wgrad(const void* x, const void* dy, const int* pair_in, const int* pair_out, const int* k_offsets,
+                         float* dw, long long n_in, long long n_out, long long n_pairs_hint, int cin, int cout, int K,
+                         void* stream);
 /* The per-view 2D backbone's convolution as a persistent TMA + tcgen05 implicit GEMM (csrc/conv_tma.cu): activations,
  * filter and output move with cp.async.bulk.tensor tiles (zero padding = TMA out-of-bounds fill, stride = tensor-map element
  * strides), accumulators live in TMEM, bias + residual + ReLU are fused into the epilogue. Replaces the cuDNN call behind
