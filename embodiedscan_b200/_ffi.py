@@ -46,6 +46,7 @@ SIGNATURES = {
     'esb_conv2d_tc_wgrad': ('ppp' + 'iiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tma_fwd': ('ppppp' + 'iiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tma_dgrad': ('ppp' + 'iiiiiiii' + 'p', 'i'),
+    'esb_stem7x7_tc': ('pppp' + 'iiii' + 'p', 'i'),
     'esb_conv2d_direct_fwd': ('ppppp' + 'iiiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_direct_dgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_direct_wgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),

@@ -263,8 +263,15 @@ class _ConvBlock2D(torch.autograd.Function):
         if not w_ohwi.is_contiguous():
             w_ohwi = w_ohwi.contiguous()
         tma = x.dtype == torch.bfloat16 and tma_channels_ok(cin) and tma_channels_ok(cout)
+        stem = (x.dtype == torch.bfloat16 and (cin, cout, kh, kw, stride, pad) == (3, 16, 7, 7, 2, 3) and res is None
+                and bias is not None and (W * 3) % 2 == 0)
         if tma:
             y = conv2d_tma(x, w_ohwi, bias, res, relu, stride, pad)
+        elif stem:       # tcgen05 with the im2col rows built in shared memory (csrc/conv_tma.cu::stem7x7_tc_kernel)
+            Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            y = torch.empty((N, cout, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+            _ffi.call('esb_stem7x7_tc', x.data_ptr(), w_ohwi.data_ptr(), bias.data_ptr(), y.data_ptr(), N, H, W,
+                      1 if relu else 0, _ffi.stream())
         else:
             Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
             y = torch.empty((N, cout, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)

@@ -401,3 +401,154 @@ extern "C" int esb_conv2d_tma_dgrad(const void* dy, const void* w_ohwi, void* dx
   return conv_tma_run(dy, w_ohwi, nullptr, nullptr, dx, n_img, Ho, Wo, cout, H, W, cin, kh, kw, 1, kh - 1 - pad, 0, true,
                       (cudaStream_t)stream_);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// The 7x7 / stride 2 / pad 3 stem on the 3-channel image (Cin = 3 cannot feed a 16-byte TMA box): the CTA stages the
+// input patch of a 16 x 8 output tile in shared memory with coalesced loads, every thread lays out ITS pixel's 147-tap row
+// as the K-major 128B-swizzled A operand (im2col in shared memory, never in HBM), one thread issues ten tcgen05.mma
+// (M=128, N=16, K=16) against the filter resident in shared memory, and the epilogue adds the folded-BN bias, applies
+// ReLU and stores 32 contiguous bytes per pixel. Persistent over tiles. Roofline: HBM (image in, 16-channel map out).
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int ST_TW = 16, ST_TH = 8;                 // output tile
+constexpr int ST_PW = 112, ST_PH = 2 * ST_TH + 5;    // patch: 112 bf16 per row (1 pad + 37 pixels x 3), 21 rows
+constexpr int ST_K = 147, ST_KPAD = 160;             // 7*7*3 taps, padded to 10 x K16
+
+__global__ void __launch_bounds__(128)
+stem7x7_tc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                  __nv_bfloat16* __restrict__ y, int n_img, int H, int W, int Ho, int Wo, int relu) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_tile = smem;                                   // 3 chunks x (128 rows x 128 B) = 48 KB
+  uint8_t* b_tile = smem + 3 * 16384;                       // 3 chunks x (16 rows x 128 B) = 6 KB
+  __nv_bfloat16* patch = (__nv_bfloat16*)(b_tile + 3 * 2048);   // 21 x 112 bf16
+  uint64_t* bar = (uint64_t*)((uint8_t*)patch + ((ST_PH * ST_PW * 2 + 15) & ~15));
+  uint32_t* tmem_slot = (uint32_t*)(bar + 1);
+
+  const int t = threadIdx.x, warp = t >> 5;
+  if (t == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 32);
+  // filter: (16, 147) bf16 -> K-major SW128 rows of three 64-wide chunks, zero beyond 147
+  for (int i = t; i < 16 * 24; i += 128) {                  // 16 rows x 24 pieces of 8 elements
+    const int n = i / 24, j = i - n * 24;                   // j = 16-byte piece index along K (0..23; 20..23 are padding)
+    uint32_t v[4] = {0u, 0u, 0u, 0u};
+    __nv_bfloat16* vp = reinterpret_cast<__nv_bfloat16*>(v);
+    for (int e = 0; e < 8; ++e) {
+      const int k = j * 8 + e;
+      if (k < ST_K) vp[e] = w[n * ST_K + k];
+    }
+    const int c = j >> 3, jj = j & 7;
+    *reinterpret_cast<uint4*>(b_tile + c * 2048 + n * 128 + ((jj ^ (n & 7)) << 4)) = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc(TC_M, 16, 0, 0);
+
+  const int tiles_w = (Wo + ST_TW - 1) / ST_TW, tiles_h = (Ho + ST_TH - 1) / ST_TH;
+  const int n_tiles = tiles_w * tiles_h * n_img;
+  const int tx = t & 15, ty = t >> 4;                       // this thread's pixel inside the tile (row m = t)
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int r = tile;
+    const int twi = r % tiles_w; r /= tiles_w;
+    const int thi = r % tiles_h;
+    const int img = r / tiles_h;
+    const int ox0 = twi * ST_TW, oy0 = thi * ST_TH;
+    // ---- input patch: rows 2*oy0-3 .. +20, elements (2*ox0-3)*3 - 1 .. +111 of the (W*3)-element image rows; 4-byte words
+    const int g0 = (2 * ox0 - 3) * 3 - 1;                   // even: words never straddle the row ends (W*3 is even)
+    const __nv_bfloat16* ximg = x + (long long)img * H * W * 3;
+    for (int i = t; i < ST_PH * (ST_PW / 2); i += 128) {
+      const int pr = i / (ST_PW / 2), pw = i - pr * (ST_PW / 2);
+      const int iy = 2 * oy0 - 3 + pr, g = g0 + 2 * pw;
+      uint32_t v = 0u;
+      if (iy >= 0 && iy < H && g >= 0 && g + 1 < W * 3) v = *reinterpret_cast<const uint32_t*>(ximg + (long long)iy * W * 3 + g);
+      reinterpret_cast<uint32_t*>(patch)[pr * (ST_PW / 2) + pw] = v;
+    }
+    __syncthreads();
+    // ---- im2col in shared memory: row t of A = the 7 x 21 window of this pixel, k = ky*21 + kx*3 + c
+    {
+      const __nv_bfloat16* base = patch + (2 * ty) * ST_PW + 6 * tx + 1;
+      const uint32_t row_off = (uint32_t)((t >> 3) * 1024 + (t & 7) * 128);
+#pragma unroll
+      for (int j = 0; j < ST_KPAD / 8; ++j) {               // 20 pieces of 8 elements
+        uint32_t v[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int k0 = j * 8 + 2 * h, k1 = k0 + 1;
+          const uint32_t lo = k0 < ST_K ? (uint32_t)__bfloat16_as_ushort(base[(k0 / 21) * ST_PW + (k0 % 21)]) : 0u;
+          const uint32_t hi = k1 < ST_K ? (uint32_t)__bfloat16_as_ushort(base[(k1 / 21) * ST_PW + (k1 % 21)]) : 0u;
+          v[h] = lo | (hi << 16);
+        }
+        const int c = j >> 3, jj = j & 7;
+        *reinterpret_cast<uint4*>(a_tile + c * 16384 + row_off + ((jj ^ (t & 7)) << 4)) = make_uint4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (t == 0) {
+      const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(b_tile);
+#pragma unroll
+      for (int kk = 0; kk < ST_KPAD / 16; ++kk)
+        umma_bf16(tmem_base, make_desc(a_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                  make_desc(b_addr + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+    tc_fence_before();
+    const int ox = ox0 + tx, oy = oy0 + ty;
+    if (ox < Wo && oy < Ho) {
+      uint32_t o[8];
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        float f0 = __uint_as_float(v[2 * h]) + bias[2 * h], f1 = __uint_as_float(v[2 * h + 1]) + bias[2 * h + 1];
+        if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+        o[h] = pack_bf16(__float_as_uint(f0), __float_as_uint(f1));
+      }
+      uint4* dst = reinterpret_cast<uint4*>(y + (((long long)img * Ho + oy) * Wo + ox) * 16);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    __syncthreads();          // the patch and the A tile are rewritten by the next iteration; TMEM reads are done
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+}  // namespace
+
+// Stem of the image backbone: y (n,Ho,Wo,16) = act(conv7x7/2/3(x (n,H,W,3), w_ohwi (16,7,7,3)) + bias), bf16 NHWC.
+extern "C" int esb_stem7x7_tc(const void* x, const void* w_ohwi, const float* bias, void* y, int n_img, int H, int W, int relu,
+                              void* stream_) {
+  ESB_CHECK_ARG(n_img >= 0 && H > 0 && W > 0 && (W * 3) % 2 == 0, "esb_stem7x7_tc: W*3 must be even (4-byte patch loads)");
+  ESB_CHECK_ARG(bias != nullptr, "esb_stem7x7_tc: bias (16 fp32) is required");
+  if (n_img == 0) return ESB_OK;
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const size_t smem = 3 * 16384 + 3 * 2048 + ((ST_PH * ST_PW * 2 + 15) & ~15) + 16 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(stem7x7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { esb_set_error("esb_stem7x7_tc: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (long long)esb_div_up(Wo, ST_TW) * esb_div_up(Ho, ST_TH) * n_img;
+  long long grid = (long long)sms * 3;
+  if (grid > n_tiles) grid = n_tiles;
+  stem7x7_tc_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream_>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)w_ohwi, bias, (__nv_bfloat16*)y, n_img, H, W, Ho, Wo, relu);
+  ESB_CUDA_LAUNCH_CHECK("stem7x7_tc_kernel");
+  return ESB_OK;
+}

@@ -123,6 +123,10 @@ int esb_conv2d_tma_fwd(const void* x, const void* w_ohwi, const float* bias, con
  * forward filter as stored (taps visited in reverse, filter read as the MN-major B operand: no transposed copy). */
 int esb_conv2d_tma_dgrad(const void* dy, const void* w_ohwi, void* dx, int n_img, int H, int W, int cin, int cout, int kh,
                          int kw, int pad, void* stream);
+/* The 7x7/2 stem on the 3-channel image as a tcgen05 implicit GEMM with the im2col rows built in shared memory
+ * (csrc/conv_tma.cu::stem7x7_tc_kernel). x (n_img,H,W,3) bf16 NHWC, w_ohwi (16,7,7,3) bf16, bias (16) fp32, y (n_img,Ho,Wo,16). */
+int esb_stem7x7_tc(const void* x, const void* w_ohwi, const float* bias, void* y, int n_img, int H, int W, int relu,
+                   void* stream);
 /* Direct (SIMT, fp32-accumulate) NHWC convolution and its gradients (csrc/conv2d_direct.cu): the fp32 parity arithmetic of
  * every 2D convolution of the image backbone, and the 7x7/2 stem on the 3-channel image in either dtype. x (n_img,H,W,cin),
  * w_ohwi (cout,kh,kw,cin), y / residual (n_img,Ho,Wo,cout) in `dtype` (ESB_F32 / ESB_BF16); bias fp32 or NULL. */

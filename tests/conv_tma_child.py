@@ -26,6 +26,37 @@ CASES = [
 ]
 
 
+def run_stem(dev):
+    """The 7x7/2 stem (tcgen05 with shared-memory im2col) through the module-level dispatch of backbones._ConvBlock2D."""
+    from embodiedscan_b200.backbones import _ConvBlock2D
+    for n, hw in ((2, (48, 64)), (3, (62, 90)), (1, (480, 640))):
+        g = torch.Generator().manual_seed(n * 7 + hw[0])
+        x = torch.randn(n, 3, *hw, generator=g).bfloat16()
+        w = (torch.randn(16, 3, 7, 7, generator=g) / 147 ** 0.5).bfloat16()
+        b = torch.randn(16, generator=g)
+        ref = F.relu(F.conv2d(x.float(), w.float(), b, 2, 3))
+        out = _ConvBlock2D.apply(x.to(dev).contiguous(memory_format=torch.channels_last),
+                                 w.to(dev).contiguous(memory_format=torch.channels_last), b.to(dev), None, True, 2, 3)
+        torch.cuda.synchronize()
+        err = float((out.float().cpu() - ref).abs().max())
+        tol = 1e-2 * max(float(ref.abs().max()), 1.0)
+        print(json.dumps(dict(kind='stem', case=[n, list(hw)], err=err, tol=tol, ok=bool(out.shape == ref.shape and err <= tol))),
+              flush=True)
+    x = torch.randn(80, 3, 480, 640, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = torch.randn(16, 3, 7, 7, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    b = torch.zeros(16, device=dev)
+    for _ in range(3):
+        _ConvBlock2D.apply(x, w, b, None, True, 2, 3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        y = _ConvBlock2D.apply(x, w, b, None, True, 2, 3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(json.dumps(dict(kind='bench_stem', us=1e3 * ms, gbs=(x.numel() + y.numel()) * 2 / ms / 1e6)), flush=True)
+
+
 def run_case(case, dev):
     from embodiedscan_b200.backbones import conv2d_tma, conv2d_tma_dgrad, ohwi
     cin, cout, k, stride, pad, hw, n, with_res = case
@@ -105,6 +136,10 @@ def main():
             run_case(case, dev)
         except Exception as e:  # noqa
             print(json.dumps(dict(kind='error', case=list(case[:5]), ok=False, err=str(e)[:300])), flush=True)
+    try:
+        run_stem(dev)
+    except Exception as e:  # noqa
+        print(json.dumps(dict(kind='error', case='stem', ok=False, err=str(e)[:300])), flush=True)
     if '--bench' in sys.argv:
         bench(dev)
 
