@@ -318,7 +318,7 @@ def main():
         for j in range(3):
             step(j)
         torch.cuda.synchronize()
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
             for j in range(2):
                 step(j)
             torch.cuda.synchronize()
@@ -326,6 +326,12 @@ def main():
             f.write(prof.key_averages().table(sort_by='cuda_time_total', row_limit=60, max_name_column_width=70))
             f.write('\n\n')
             f.write(prof.key_averages().table(sort_by='self_cpu_time_total', row_limit=40, max_name_column_width=70))
+            f.write('\n\n# by call site (innermost 3 Python frames), sorted by device time, then by host time\n')
+            f.write(prof.key_averages(group_by_stack_n=3).table(sort_by='cuda_time_total', row_limit=70,
+                                                                max_name_column_width=50, max_src_column_width=110))
+            f.write('\n\n')
+            f.write(prof.key_averages(group_by_stack_n=3).table(sort_by='self_cpu_time_total', row_limit=70,
+                                                                max_name_column_width=50, max_src_column_width=110))
         log('torch profile written')
     for j in range(n_distinct):      # setup pass: one step per distinct batch shape (allocator / cuDNN plan caches)
         step(j)

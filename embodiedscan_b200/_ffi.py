@@ -41,6 +41,7 @@ SIGNATURES = {
     'esb_act_fwd': ('ppqiip', 'i'),
     'esb_bias_act_fwd': ('ppppqiiip', 'i'),
     'esb_act_bwd': ('pppqiip', 'i'),
+    'esb_gather2_rows': ('ppqpppqiip', 'i'),
     'esb_conv2d_tc_fwd': ('ppppp' + 'iiiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tc_dgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tc_wgrad': ('ppp' + 'iiiiiiiii' + 'p', 'i'),

@@ -349,6 +349,34 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y
   }
 }
 
+// out[r, :] = a[ia(r), :] + b[ib[r], :] with ia(r) = ia ? ia[r] : (r < na ? r : -1); a negative index contributes zeros.
+// One thread per (row, 8-channel piece): the row gather of unions (A + B on different coordinate maps), of their gradients
+// and of every `x[idx]` on the path; each output element is written once (no atomics).
+template <typename T>
+__global__ void gather2_rows_kernel(const T* __restrict__ a, const int* __restrict__ ia, long long na, const T* __restrict__ b,
+                                    const int* __restrict__ ib, T* __restrict__ out, long long n_vec, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vec) return;
+  const int cv = C / 8;
+  const long long r = i / cv;
+  const int c = (int)(i - r * cv) * 8;
+  const long long ra = ia ? (long long)ia[r] : (r < na ? r : -1);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (ra >= 0) load8<T>(a + ra * C + c, v);
+  if (b != nullptr) {
+    const int rb = ib[r];
+    if (rb >= 0) {
+      float w[8];
+      load8<T>(b + (long long)rb * C + c, w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += w[e];
+    }
+  }
+  store8<T>(out + r * C + c, v);
+}
+
 }  // namespace
 
 #define DISPATCH_T(dtype, ...)                         \
@@ -478,5 +506,19 @@ extern "C" int esb_act_bwd(const void* dy, const void* y, void* dx, long long n,
   DISPATCH_T(dtype, (act_bwd_kernel<T><<<esb_div_up(n, 256 * 8), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)dy, (const T*)y, (T*)dx, n, act)));
   ESB_CUDA_LAUNCH_CHECK("act_bwd_kernel");
+  return ESB_OK;
+}
+
+// out (n, C) = a[ia] + b[ib] row-wise (see gather2_rows_kernel). ia may be NULL (identity on the first na rows), b / ib may be
+// NULL (plain gather). C % 8 == 0.
+extern "C" int esb_gather2_rows(const void* a, const int* ia, long long na, const void* b, const int* ib, void* out, long long n,
+                                int C, int dtype, void* stream) {
+  ESB_CHECK_ARG(C > 0 && C % 8 == 0, "esb_gather2_rows: C must be a positive multiple of 8");
+  ESB_CHECK_ARG((b == nullptr) == (ib == nullptr), "esb_gather2_rows: b and ib go together");
+  const long long n_vec = n * (C / 8);
+  if (n_vec == 0) return ESB_OK;
+  DISPATCH_T(dtype, (gather2_rows_kernel<T><<<esb_div_up(n_vec, 256), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)a, ia, na, (const T*)b, ib, (T*)out, n_vec, C)));
+  ESB_CUDA_LAUNCH_CHECK("gather2_rows_kernel");
   return ESB_OK;
 }

@@ -260,10 +260,15 @@ class CoordinateManager:
             call('esb_hash_lookup', ptr(B.coords), B.n, ptr(A.keys), ptr(A.vals), A.cap, ptr(idx), stream())
             new = idx < 0
             rank = torch.cumsum(new.to(torch.int32), 0, dtype=torch.int32) - 1 + A.n
-            map_b = torch.where(new, rank, idx).to(torch.int64)
+            map_b32 = torch.where(new, rank, idx)
+            map_b = map_b32.to(torch.int64)
             coords = torch.cat([A.coords, B.coords[new]], 0)
             key = self.insert_unique(coords, A.stride)
+            # inverse: union row -> row of B (or -1); the union add is then ONE gather pass, no atomics
+            inv_b = torch.full((coords.shape[0], ), -1, dtype=torch.int32, device=self.device)
+            inv_b[map_b] = torch.arange(B.n, dtype=torch.int32, device=self.device)
             self.kmaps[ck] = (key, map_b)
+            self.kmaps[('union_maps', a_key, b_key)] = (map_b32.contiguous(), inv_b)
         return self.kmaps[ck]
 
 
@@ -440,6 +445,33 @@ def weight_operand(p: torch.Tensor, dtype) -> torch.Tensor:
     if dtype == torch.bfloat16 and p.is_cuda and p.dtype == torch.float32:
         return _ShadowCast.apply(p)
     return p.to(dtype)
+
+
+class _UnionAdd(torch.autograd.Function):
+    """out = A (rows 0..nA of the union) + B scattered by map_b, as one row-gather pass (csrc/spops.cu::gather2_rows_kernel);
+    backward: dA = the first nA rows of dOut, dB = dOut gathered by map_b."""
+
+    @staticmethod
+    def forward(ctx, fa, fb, map_b32, inv_b, n_union):
+        fa, fb = fa.contiguous(), fb.contiguous()
+        out = torch.empty((n_union, fa.shape[1]), dtype=fa.dtype, device=fa.device)
+        call('esb_gather2_rows', ptr(fa), None, fa.shape[0], ptr(fb), ptr(inv_b), ptr(out), n_union, fa.shape[1],
+             _ffi.dtype_code(fa.dtype), stream())
+        ctx.save_for_backward(map_b32)
+        ctx.na = fa.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (map_b32, ) = ctx.saved_tensors
+        dout = dout.contiguous()
+        da = dout[:ctx.na] if ctx.needs_input_grad[0] else None
+        db = None
+        if ctx.needs_input_grad[1]:
+            db = torch.empty((map_b32.shape[0], dout.shape[1]), dtype=dout.dtype, device=dout.device)
+            call('esb_gather2_rows', ptr(dout), ptr(map_b32), dout.shape[0], None, None, ptr(db), map_b32.shape[0],
+                 dout.shape[1], _ffi.dtype_code(dout.dtype), stream())
+        return da, db, None, None, None
 
 
 class _MaxPool(torch.autograd.Function):
@@ -648,8 +680,12 @@ class SparseTensor:
             return self.replace_feature(self.F + other.F)
         key, map_b = mgr.union_key(self.coordinate_map_key, other.coordinate_map_key)
         n = mgr.maps[key].n
-        pad = torch.zeros((n - self.F.shape[0], self.F.shape[1]), dtype=self.F.dtype, device=self.F.device)
-        out = torch.cat([self.F, pad], 0).index_add(0, map_b, other.F.to(self.F.dtype))
+        if self.F.is_cuda and self.F.shape[1] % 8 == 0 and self.F.dtype in (torch.float32, torch.bfloat16):
+            map_b32, inv_b = mgr.kmaps[('union_maps', self.coordinate_map_key, other.coordinate_map_key)]
+            out = _UnionAdd.apply(self.F, other.F.to(self.F.dtype), map_b32, inv_b, n)
+        else:
+            pad = torch.zeros((n - self.F.shape[0], self.F.shape[1]), dtype=self.F.dtype, device=self.F.device)
+            out = torch.cat([self.F, pad], 0).index_add(0, map_b, other.F.to(self.F.dtype))
         return SparseTensor(out, coordinate_map_key=key, coordinate_manager=mgr)
 
     def features_at_coordinates(self, query: torch.Tensor) -> torch.Tensor:

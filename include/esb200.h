@@ -85,6 +85,11 @@ int esb_act_fwd(const void* x, void* y, long long n, int act, int dtype, void* s
 int esb_bias_act_fwd(const void* x, const float* bias, const void* res, void* y, long long rows, int C, int act,
                      int dtype, void* stream);
 int esb_act_bwd(const void* dy, const void* y, void* dx, long long n, int act, int dtype, void* stream);
+/* out (n,C) = a[ia] + b[ib] row-wise; a negative index contributes zeros. ia NULL = identity on the first na rows; b/ib NULL =
+ * plain gather. The union `A + B` of sparse tensors on different coordinate maps (ME `__add__`, fcaf3d_head.py:1011) and the
+ * row gathers of its backward. C % 8 == 0. */
+int esb_gather2_rows(const void* a, const int* ia, long long na, const void* b, const int* ib, void* out, long long n, int C,
+                     int dtype, void* stream);
 /* EXPERIMENTAL (compiled, not on the measured path yet): the folded conv+BN(+residual)(+ReLU) block of the per-view 2D
  * ResNet (mmdet.ResNet called at embodiedscan/models/detectors/sparse_featfusion_single_stage.py:130-136) as ONE
  * tcgen05 implicit GEMM. x (n_img,H,W,cin) bf16 NHWC; w_ohwi (cout, r_pad) bf16 = the filter in (ky,kx,ci) order,
