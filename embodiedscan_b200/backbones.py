@@ -172,15 +172,29 @@ def conv2d_tma(x: torch.Tensor, w_ohwi: torch.Tensor, bias, res, relu: bool, str
     return y
 
 
-def conv2d_tma_dgrad(dy: torch.Tensor, w_ohwi: torch.Tensor, in_hw, pad: int) -> torch.Tensor:
-    """dL/dx of a STRIDE-1 ``F.conv2d(x, w, pad)`` with the same kernel (flipped taps, filter read MN-major)."""
+def conv2d_tma_wgrad(x: torch.Tensor, dy: torch.Tensor, w_shape, stride: int, pad: int) -> torch.Tensor:
+    """dL/dw of ``F.conv2d(x, w, stride, pad)`` with TMA-fed MN-major operands (csrc/conv_tma.cu::conv_tma_wgrad_kernel);
+    x (N,Cin,H,W), dy (N,Cout,Ho,Wo) bf16 channels_last -> (Cout,Cin,kh,kw) fp32 view of the (kh*kw*Cin, Cout) accumulator."""
+    from . import _ffi
+    cout, cin, kh, kw = w_shape
+    assert x.dtype == dy.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last) \
+        and dy.is_contiguous(memory_format=torch.channels_last)
+    dw_t = torch.zeros((kh * kw * cin, cout), dtype=torch.float32, device=x.device)
+    _ffi.call('esb_conv2d_tma_wgrad', x.data_ptr(), dy.data_ptr(), dw_t.data_ptr(), x.shape[0], x.shape[2], x.shape[3], cin,
+              cout, kh, kw, stride, pad, _ffi.stream())
+    return dw_t.view(kh, kw, cin, cout).permute(3, 2, 0, 1)
+
+
+def conv2d_tma_dgrad(dy: torch.Tensor, w_ohwi: torch.Tensor, in_hw, pad: int, stride: int = 1) -> torch.Tensor:
+    """dL/dx of ``F.conv2d(x, w, stride, pad)`` (stride 1 or 2) with the same kernel: flipped taps, filter read MN-major;
+    stride 2 = one launch per parity class of dx (strided TMA stores)."""
     from . import _ffi
     assert dy.is_cuda and dy.dtype == torch.bfloat16 and dy.is_contiguous(memory_format=torch.channels_last)
     cout, kh, kw, cin = w_ohwi.shape
     H, W = in_hw
     dx = torch.empty((dy.shape[0], cin, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
     _ffi.call('esb_conv2d_tma_dgrad', dy.data_ptr(), w_ohwi.data_ptr(), dx.data_ptr(), dy.shape[0], H, W, cin, cout, kh, kw,
-              pad, _ffi.stream())
+              stride, pad, _ffi.stream())
     return dx
 
 
@@ -301,8 +315,8 @@ class _ConvBlock2D(torch.autograd.Function):
         code = _ffi.dtype_code(x.dtype)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            if tma and stride == 1:
-                dx = conv2d_tma_dgrad(g, w_ohwi, (H, W), pad)
+            if tma and stride in (1, 2):
+                dx = conv2d_tma_dgrad(g, w_ohwi, (H, W), pad, stride)
             elif tma:
                 dx = conv2d_tc_dgrad(g, w_ohwi.permute(0, 3, 1, 2), (H, W), stride, pad)
             else:
@@ -311,7 +325,7 @@ class _ConvBlock2D(torch.autograd.Function):
                           kw, stride, pad, code, _ffi.stream())
         if ctx.needs_input_grad[1]:
             if tma:
-                dw = conv2d_tc_wgrad(x, g, (cout, cin, kh, kw), stride, pad)          # (Cout,Cin,kh,kw) view, fp32
+                dw = conv2d_tma_wgrad(x, g, (cout, cin, kh, kw), stride, pad)         # (Cout,Cin,kh,kw) view, fp32
             else:
                 dwo = torch.zeros((cout, kh, kw, cin), dtype=torch.float32, device=x.device)
                 _ffi.call('esb_conv2d_direct_wgrad', x.data_ptr(), g.data_ptr(), dwo.data_ptr(), N, H, W, cin, cout, kh, kw,
@@ -537,18 +551,26 @@ class ResNet(nn.Module):
 
     # ---- CUDA graphs: the image branch has static shapes (views x H x W), so its ~60 forward launches and ~150 backward
     # launches replay as TWO graph launches per step; the host thread is free for the data-dependent 3D plan.
+    def _graph_lists(self):
+        c = self.__dict__.get('_graph_cache')
+        if c is None:        # module / tensor lists are walked once (named_modules costs milliseconds per step otherwise)
+            c = self.__dict__['_graph_cache'] = dict(bns=[m for m in self.modules() if isinstance(m, nn.BatchNorm2d)],
+                                                     params=list(self.parameters()), buffers=list(self.buffers()))
+        return c
+
     def _graphable(self, x):
         import os
+        c = self._graph_lists()
         return (x.is_cuda and self.training and torch.is_grad_enabled() and x.dtype == torch.bfloat16
                 and conv2d_backend() == 'own' and os.environ.get('ESB200_GRAPH2D', '1') != '0'
                 and not torch.cuda.is_current_stream_capturing()
-                and all(not b.training for b in self.modules() if isinstance(b, nn.BatchNorm2d))
-                and any(p.requires_grad for p in self.parameters()))
+                and all(not b.training for b in c['bns']) and any(p.requires_grad for p in c['params']))
 
     def _graph_signature(self):
         # frozen tensors are baked into the captured constants (folded filters): any in-place change invalidates the graph
-        return tuple(t._version for t in self.buffers()) + tuple(p._version for p in self.parameters() if not p.requires_grad) \
-            + tuple(p.data_ptr() for p in self.parameters() if p.requires_grad)
+        c = self._graph_lists()
+        return tuple(t._version for t in c['buffers']) + tuple(p._version for p in c['params'] if not p.requires_grad) \
+            + tuple(p.data_ptr() for p in c['params'] if p.requires_grad)
 
     def _graphed_forward(self, x):
         graphs = self.__dict__.setdefault('_graphs', {})

@@ -29,10 +29,14 @@ struct ConvGeom {
   int tiles_w, tiles_h, tiles_n, n_blocks;   // tile grid; n_blocks = Cout / N_TILE
   int TW, TH, TN;                            // output pixels per tile along w, h, image
   int Wo, Ho, N;                             // output extent
-  int kh, kw, stride, pad;
+  int stride;                                // spacing of the A-box origin per output pixel (element strides of the tensor map)
   int cin, bc, nchunk, group;                // reduction channels per tap, channels per sub-tile, cin / bc, sub-tiles per stage
-  int cout, relu, flip;
+  int cout, relu;
   int stages;
+  // filter taps as a table: input offset of the tap relative to (output pixel * stride) and its index in the stored filter.
+  // forward: (kx - pad, ky - pad, tap); stride-1 dgrad: flipped taps; stride-2 dgrad: the taps of one output parity class.
+  int ntaps;
+  short tap_dx[16], tap_dy[16], tap_w[16];
 };
 
 constexpr int EPI_THREADS = 128;
@@ -64,8 +68,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int taps = g.kh * g.kw;
-  const int n_sub = taps * g.nchunk;                           // sub-tiles (tap, channel chunk) per output tile
+  const int n_sub = g.ntaps * g.nchunk;                        // sub-tiles (tap, channel chunk) per output tile
   const int n_it = (n_sub + g.group - 1) / g.group;            // pipeline stages per output tile
   const int bcb = g.bc * 2;                                    // bytes per sub-tile row
   const int rows_box = g.TW * g.TH * g.TN;
@@ -103,7 +106,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
         const int th = t % g.tiles_h; t /= g.tiles_h;
         const int tn = t % g.tiles_n; t /= g.tiles_n;
         const int n0 = t * N_TILE;
-        const int x0 = tw * g.TW * g.stride - g.pad, y0 = th * g.TH * g.stride - g.pad, img0 = tn * g.TN;
+        const int x0 = tw * g.TW * g.stride, y0 = th * g.TH * g.stride, img0 = tn * g.TN;
         for (int i = 0; i < n_it; ++i, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
@@ -115,9 +118,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
           for (int j = 0; j < cnt; ++j) {
             const int q = q0 + j;
             const int tap = q / g.nchunk, ch = (q - tap * g.nchunk) * g.bc;
-            const int ky = tap / g.kw, kx = tap - ky * g.kw;
-            tma_load_4d(&tmx, &full_bar[s], a_base + j * (128 * bcb), ch, x0 + kx, y0 + ky, img0);
-            const int wtap = g.flip ? taps - 1 - tap : tap;
+            tma_load_4d(&tmx, &full_bar[s], a_base + j * (128 * bcb), ch, x0 + g.tap_dx[tap], y0 + g.tap_dy[tap], img0);
+            const int wtap = g.tap_w[tap];
             if (!B_MN) {           // rows = output channels, columns = (tap, input channel): K-major B
               tma_load_2d(&tmw, &full_bar[s], b_base + j * b_sub_bytes, wtap * g.cin + ch, n0);
             } else {               // rows = reduction channels, columns = (tap, output channel): MN-major B, <= 64 columns per box
@@ -281,7 +283,7 @@ int launch(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tm
            ConvGeom g, cudaStream_t stream) {
   constexpr int CB_COLS = N_TILE < 64 ? N_TILE : 64;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + N_TILE * 128;
-  const int n_it = (g.kh * g.kw * g.nchunk + g.group - 1) / g.group;
+  const int n_it = (g.ntaps * g.nchunk + g.group - 1) / g.group;
   (void)n_it;
   // the stage ring runs ahead ACROSS output tiles (persistent CTA), so its depth is set by shared memory, not by the filter:
   // two CTAs per SM up to N_TILE = 64 (~100 KB each), one CTA per SM above
@@ -304,13 +306,14 @@ int launch(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tm
   return ESB_OK;
 }
 
-// in (N, Hi, Wi, Ci) -> out (N, Ho, Wo, Co); w_rows x w_cols is the filter matrix as stored (OHWI: Co rows, kh*kw*Ci columns)
+// One launch: `in` (N, Hi, Wi, Ci) -> `out` viewed as (N, Ho, Wo, Co) with the given byte strides (a parity class of dx is a
+// strided view), taps from the table in `g`. taps_total = kh*kw of the stored filter (extent of its tensor map).
 int conv_tma_run(const void* in, const void* w, const float* bias, const void* res, void* out, int N, int Hi, int Wi, int Ci,
-                 int Ho, int Wo, int Co, int kh, int kw, int stride, int pad, int relu, bool dgrad, cudaStream_t stream) {
-  ConvGeom g{};
+                 int Ho, int Wo, int Co, int taps_total, int stride, int relu, bool dgrad, ConvGeom g,
+                 unsigned long long out_sw, unsigned long long out_sh, unsigned long long out_sn, cudaStream_t stream) {
   g.Wo = Wo; g.Ho = Ho; g.N = N;
-  g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad;
-  g.cin = Ci; g.cout = Co; g.relu = relu; g.flip = dgrad ? 1 : 0;
+  g.stride = stride;
+  g.cin = Ci; g.cout = Co; g.relu = relu;
   g.bc = Ci >= 64 ? 64 : Ci;
   g.nchunk = Ci / g.bc;
   g.group = 64 / g.bc;
@@ -327,25 +330,24 @@ int conv_tma_run(const void* in, const void* w, const float* bias, const void* r
     int rc = esb_tma_encode(&tmx, in, 4, dims, str, box, es, g.bc * 2 >= 128 ? 128 : g.bc * 2);
     if (rc != ESB_OK) return rc;
   }
-  const int taps = kh * kw;
   if (!dgrad) {   // OHWI (Co, taps*Ci): box {bc, n_tile}
-    unsigned long long dims[2] = {(unsigned long long)taps * Ci, (unsigned long long)Co};
-    unsigned long long str[1] = {(unsigned long long)taps * Ci * 2};
+    unsigned long long dims[2] = {(unsigned long long)taps_total * Ci, (unsigned long long)Co};
+    unsigned long long str[1] = {(unsigned long long)taps_total * Ci * 2};
     unsigned box[2] = {(unsigned)g.bc, (unsigned)n_tile};
     int rc = esb_tma_encode(&tmw, w, 2, dims, str, box, nullptr, g.bc * 2 >= 128 ? 128 : g.bc * 2);
     if (rc != ESB_OK) return rc;
-  } else {        // the forward filter OHWI (Ci_fwd = Co here ... ) read as MN-major B: rows = reduction channel (Ci of this GEMM)
+  } else {        // the forward filter (rows = its output channels = this GEMM's reduction) read as the MN-major B operand
     const int na = n_tile < 64 ? n_tile : 64;
-    unsigned long long dims[2] = {(unsigned long long)taps * Co, (unsigned long long)Ci};
-    unsigned long long str[1] = {(unsigned long long)taps * Co * 2};
+    unsigned long long dims[2] = {(unsigned long long)taps_total * Co, (unsigned long long)Ci};
+    unsigned long long str[1] = {(unsigned long long)taps_total * Co * 2};
     unsigned box[2] = {(unsigned)na, (unsigned)g.bc};
     int rc = esb_tma_encode(&tmw, w, 2, dims, str, box, nullptr, na * 2);
     if (rc != ESB_OK) return rc;
   }
-  {   // output store: {Co, Wo, Ho, N}, box {<=64 channels, TW, TH, TN}
+  {   // output store: {Co, Wo, Ho, N} with the caller's strides, box {<=64 channels, TW, TH, TN}
     const int cb = n_tile < 64 ? n_tile : 64;
     unsigned long long dims[4] = {(unsigned long long)Co, (unsigned long long)Wo, (unsigned long long)Ho, (unsigned long long)N};
-    unsigned long long str[3] = {(unsigned long long)Co * 2, (unsigned long long)Wo * Co * 2, (unsigned long long)Ho * Wo * Co * 2};
+    unsigned long long str[3] = {out_sw, out_sh, out_sn};
     unsigned box[4] = {(unsigned)cb, (unsigned)g.TW, (unsigned)g.TH, (unsigned)g.TN};
     int rc = esb_tma_encode(&tmy, out, 4, dims, str, box, nullptr, cb * 2);
     if (rc != ESB_OK) return rc;
@@ -383,23 +385,58 @@ extern "C" int esb_conv2d_tma_fwd(const void* x, const void* w_ohwi, const float
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tma_fwd: empty output");
   if (n_img == 0) return ESB_OK;
-  return conv_tma_run(x, w_ohwi, bias, residual, y, n_img, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad, relu, false,
+  ESB_CHECK_ARG(kh * kw <= 16, "esb_conv2d_tma_fwd: at most 16 filter taps");
+  ConvGeom g{};
+  g.ntaps = kh * kw;
+  for (int t = 0; t < g.ntaps; ++t) {
+    g.tap_dx[t] = (short)(t % kw - pad);
+    g.tap_dy[t] = (short)(t / kw - pad);
+    g.tap_w[t] = (short)t;
+  }
+  return conv_tma_run(x, w_ohwi, bias, residual, y, n_img, H, W, cin, Ho, Wo, cout, kh * kw, stride, relu, false, g,
+                      (unsigned long long)cout * 2, (unsigned long long)Wo * cout * 2, (unsigned long long)Ho * Wo * cout * 2,
                       (cudaStream_t)stream_);
 }
 
-// Input gradient of a STRIDE-1 convolution: dx (n,H,W,cin) from dy (n,Ho,Wo,cout) and the forward filter w_ohwi as stored
-// (taps visited in reverse, filter read as the MN-major B operand).
+// Input gradient of a convolution with stride 1 or 2: dx (n,H,W,cin) from dy (n,Ho,Wo,cout) and the forward filter w_ohwi as
+// stored (read as the MN-major B operand). Stride 1: one launch with the taps flipped. Stride 2: dx splits into the four
+// parity classes of (h, w); each class is a stride-1 convolution of dy with the taps of matching parity, stored through a
+// tensor map whose strides skip every other pixel — every dx element is still written exactly once, no atomics, no memset
+// except for classes no tap reaches (1x1 / stride 2).
 extern "C" int esb_conv2d_tma_dgrad(const void* dy, const void* w_ohwi, void* dx, int n_img, int H, int W, int cin, int cout,
-                                    int kh, int kw, int pad, void* stream_) {
+                                    int kh, int kw, int stride, int pad, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
   ESB_CHECK_ARG(channels_ok(cin) && channels_ok(cout), "esb_conv2d_tma_dgrad: channels must be 16, 32 or a multiple of 64");
   ESB_CHECK_ARG(cin <= 256 ? (cin & (cin - 1)) == 0 : cin % 256 == 0, "esb_conv2d_tma_dgrad: Cin must be a power of two <= 256 or a multiple of 256");
-  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && pad >= 0 && pad < kh && pad < kw, "esb_conv2d_tma_dgrad: bad filter geometry");
-  const int Ho = H + 2 * pad - kh + 1, Wo = W + 2 * pad - kw + 1;
+  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && kh * kw <= 16 && pad >= 0 && pad < kh && pad < kw && (stride == 1 || stride == 2),
+                "esb_conv2d_tma_dgrad: bad filter geometry");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tma_dgrad: empty output");
   if (n_img == 0) return ESB_OK;
-  // dx = conv(dy, flipped filter) with padding kh-1-pad; reduction channels = cout, output channels = cin
-  return conv_tma_run(dy, w_ohwi, nullptr, nullptr, dx, n_img, Ho, Wo, cout, H, W, cin, kh, kw, 1, kh - 1 - pad, 0, true,
-                      (cudaStream_t)stream_);
+  const unsigned long long px = (unsigned long long)cin * 2, row = (unsigned long long)W * px, img = (unsigned long long)H * row;
+  if (stride == 2 && (kh < 2 || kw < 2))     // a 1-wide filter leaves whole parity classes of dx untouched: they are zero
+    ESB_CUDA_CALL(cudaMemsetAsync(dx, 0, (size_t)n_img * img, stream));
+  for (int ph = 0; ph < stride; ++ph)
+    for (int pw = 0; pw < stride; ++pw) {
+      const int Hc = (H - ph + stride - 1) / stride, Wc = (W - pw + stride - 1) / stride;    // pixels of this parity class
+      if (Hc <= 0 || Wc <= 0) continue;
+      ConvGeom g{};
+      for (int ky = 0; ky < kh; ++ky)
+        for (int kx = 0; kx < kw; ++kx) {
+          const int ny = ph + pad - ky, nx = pw + pad - kx;      // dy pixel = (stride * i + n) / stride for class pixel i
+          if (((ny % stride) + stride) % stride != 0 || ((nx % stride) + stride) % stride != 0) continue;
+          g.tap_dx[g.ntaps] = (short)(nx >= 0 ? nx / stride : -((-nx) / stride));
+          g.tap_dy[g.ntaps] = (short)(ny >= 0 ? ny / stride : -((-ny) / stride));
+          g.tap_w[g.ntaps] = (short)(ky * kw + kx);
+          ++g.ntaps;
+        }
+      uint8_t* base = (uint8_t*)dx + (unsigned long long)ph * row + (unsigned long long)pw * px;
+      if (g.ntaps == 0) continue;                               // no tap reaches this class: zeroed by the memset above
+      int rc = conv_tma_run(dy, w_ohwi, nullptr, nullptr, base, n_img, Ho, Wo, cout, Hc, Wc, cin, kh * kw, 1, 0, true, g,
+                            (unsigned long long)stride * px, (unsigned long long)stride * row, img, stream);
+      if (rc != ESB_OK) return rc;
+    }
+  return ESB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -550,5 +587,240 @@ extern "C" int esb_stem7x7_tc(const void* x, const void* w_ohwi, const float* bi
   stem7x7_tc_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream_>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)w_ohwi, bias, (__nv_bfloat16*)y, n_img, H, W, Ho, Wo, relu);
   ESB_CUDA_LAUNCH_CHECK("stem7x7_tc_kernel");
+  return ESB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Weight gradient of the dense NHWC convolution, TMA-fed: dW^T[(tap, ci), co] = sum over output pixels of
+// x[pixel shifted by tap, ci] * dy[pixel, co]. The pixels are the reduction dimension: a pipeline stage holds a box of exactly
+// 64 output pixels (TN x TH x TW, powers of two) of dy and, for every (tap, channel slice) "atom" of the CTA's 128-row slice
+// of the filter, the same box of x at the tap's offset (zero padding and ragged edges = TMA out-of-bounds zeros on BOTH
+// operands, stride 2 = element strides). Both boxes land as [pixel][channel] rows = the MN-major operands tcgen05 takes
+// directly (no transpose anywhere). A CTA accumulates its share of the pixel tiles in TMEM and adds its 128 x N_TILE fp32
+// tile to dW^T with coalesced 16-byte vector atomics.
+// CTA = (pixel-tile range) x (128-row slice of (tap, ci)) x (N_TILE slice of co). Warps: 0 producer, 1 MMA, 2..5 epilogue.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct WgradGeom {
+  int tiles_w, tiles_h, tiles_n;     // pixel-tile grid over the OUTPUT pixels
+  int TW, TH, TN;                    // TW*TH*TN == 64
+  int kh, kw, stride, pad;
+  int cin, cout, aw, atoms_per_slice, chunks_per_tap;   // aw = channels per atom = min(cin, 64)
+  int stages, tiles_per_cta;
+};
+
+template <int N_TILE>
+__global__ void __launch_bounds__(THREADS)
+conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmdy,
+                      float* __restrict__ dw, const WgradGeom g) {
+  constexpr int NA = N_TILE < 64 ? N_TILE : 64;                // columns per B atom
+  constexpr int A_BYTES = 64 * 256;                            // 64 pixels x 128 filter rows
+  constexpr int B_BYTES = 64 * N_TILE * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = N_TILE < 32 ? 32 : N_TILE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int STAGES = g.stages;
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = g.kh * g.kw;
+  const int n_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  const int t_beg = blockIdx.x * g.tiles_per_cta;
+  const int t_end = min(n_tiles, t_beg + g.tiles_per_cta);
+  if (t_beg >= n_tiles) return;                                // uniform for the whole CTA
+  const int total = t_end - t_beg;
+  const int slice = blockIdx.y, co0 = blockIdx.z * N_TILE;
+  const int awb = g.aw * 2;                                    // bytes per A row
+  const int atom0 = slice * g.atoms_per_slice;
+  const int n_atoms_total = taps * g.chunks_per_tap;
+  const int n_valid = min(g.atoms_per_slice, n_atoms_total - atom0);
+  const uint32_t a_atom_bytes = 64u * awb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmdy);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        int t = t_beg + it;
+        const int tw = t % g.tiles_w; t /= g.tiles_w;
+        const int th = t % g.tiles_h; t /= g.tiles_h;
+        const int ox0 = tw * g.TW, oy0 = th * g.TH, img0 = t * g.TN;
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], (uint32_t)n_valid * a_atom_bytes + B_BYTES);
+        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_base = a_base + A_BYTES;
+        for (int a = 0; a < n_valid; ++a) {
+          const int ga = atom0 + a;
+          const int tap = ga / g.chunks_per_tap, ch0 = (ga - tap * g.chunks_per_tap) * g.aw;
+          const int ky = tap / g.kw, kx = tap - ky * g.kw;
+          tma_load_4d(&tmx, &full_bar[s], a_base + a * a_atom_bytes, ch0, ox0 * g.stride - g.pad + kx, oy0 * g.stride - g.pad + ky,
+                      img0);
+        }
+#pragma unroll
+        for (int b = 0; b < N_TILE / NA; ++b)
+          tma_load_4d(&tmdy, &full_bar[s], b_base + b * (64 * NA * 2), co0 + b * NA, ox0, oy0, img0);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, N_TILE, 1, 1);
+    const uint32_t a_layout = umma_layout_of(awb), b_layout = umma_layout_of(NA * 2);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&full_bar[s], (it / STAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)                           // 16 pixels per MMA
+          umma_bf16(tmem_base, make_desc_sw(a_addr + kk * 16 * awb, a_atom_bytes, 8 * awb, a_layout),
+                    make_desc_sw(b_addr + kk * 16 * (NA * 2), 64 * NA * 2, 8 * (NA * 2), b_layout), idesc,
+                    (it > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (it == total - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else {
+    const int quad = warp & 3;
+    const int et = quad * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    constexpr int PITCH = N_TILE + 4;
+    float* stg = reinterpret_cast<float*>(smem);
+#pragma unroll 1
+    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      constexpr int W32 = N_TILE < 32 ? N_TILE : 32;
+      uint32_t v[32];
+      if (W32 == 32) tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      else tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int q = 0; q < W32 / 4; ++q)
+        *reinterpret_cast<float4*>(stg + et * PITCH + c0 + 4 * q) =
+            make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                        __uint_as_float(v[4 * q + 3]));
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int rows_valid = n_valid * g.aw;                       // accumulator rows backed by loaded atoms
+    for (int rr = 0; rr < 32; ++rr) {
+      const int r = quad * 32 + rr;
+      if (r >= rows_valid) break;
+      // row r of the slice = atom r / aw, channel r % aw  ->  filter row (tap * cin + ch)
+      const int ga = atom0 + r / g.aw;
+      const int tap = ga / g.chunks_per_tap, ch = (ga - tap * g.chunks_per_tap) * g.aw + (r % g.aw);
+      float* dwrow = dw + ((long long)tap * g.cin + ch) * g.cout + co0;
+      for (int c = lane * 4; c < N_TILE; c += 128)
+        atomicAdd(reinterpret_cast<float4*>(dwrow + c), *reinterpret_cast<const float4*>(stg + r * PITCH + c));
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int N_TILE>
+int launch_wgrad_tma(const CUtensorMap& tmx, const CUtensorMap& tmdy, float* dw, WgradGeom g, int slices, int n_blocks,
+                     cudaStream_t stream) {
+  constexpr int STAGE_BYTES = 64 * 256 + 64 * N_TILE * 2;
+  int stages = (100 * 1024) / STAGE_BYTES;
+  const int need = (128 * (N_TILE + 4) * 4 + STAGE_BYTES - 1) / STAGE_BYTES;      // the epilogue reuses the stage buffers
+  stages = stages < need ? need : stages > 6 ? 6 : stages;
+  g.stages = stages;
+  const size_t smem = (size_t)stages * STAGE_BYTES + (2 * stages + 1) * 8 + 16 + 1024;
+  auto kern = conv_tma_wgrad_kernel<N_TILE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { esb_set_error("conv_tma_wgrad: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
+  const long long n_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
+  // ~2 CTAs per SM in total; every CTA walks a contiguous range of pixel tiles
+  long long splits = (2LL * 148 + (long long)slices * n_blocks - 1) / ((long long)slices * n_blocks);
+  if (splits > n_tiles) splits = n_tiles;
+  if (splits < 1) splits = 1;
+  g.tiles_per_cta = (int)((n_tiles + splits - 1) / splits);
+  dim3 grid((unsigned)((n_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta), slices, n_blocks);
+  kern<<<grid, THREADS, smem, stream>>>(tmx, tmdy, dw, g);
+  return ESB_OK;
+}
+
+}  // namespace
+
+// dw_t (kh*kw*cin, cout) fp32, ZEROED BY THE CALLER: dW[co, ci, ky, kx] = dw_t[(ky*kw + kx)*cin + ci, co].
+// x (n,H,W,cin), dy (n,Ho,Wo,cout) bf16 NHWC; cin, cout in {16, 32, 64, 128, 256, 512, ...}.
+extern "C" int esb_conv2d_tma_wgrad(const void* x, const void* dy, float* dw_t, int n_img, int H, int W, int cin, int cout,
+                                    int kh, int kw, int stride, int pad, void* stream_) {
+  ESB_CHECK_ARG(channels_ok(cin) && channels_ok(cout), "esb_conv2d_tma_wgrad: channels must be 16, 32 or a multiple of 64");
+  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && stride >= 1 && stride <= 8 && pad >= 0, "esb_conv2d_tma_wgrad: bad filter geometry");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tma_wgrad: empty output");
+  if (n_img == 0) return ESB_OK;
+  WgradGeom g{};
+  g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.cin = cin; g.cout = cout;
+  g.aw = cin < 64 ? cin : 64;
+  g.atoms_per_slice = 128 / g.aw;
+  g.chunks_per_tap = cin / g.aw;
+  // pixel box of exactly 64 output pixels (powers of two): the one wasting the fewest zero-filled pixels
+  double best = -1.0;
+  for (int tw = 1; tw <= 64; tw *= 2)
+    for (int th = 1; tw * th <= 64; th *= 2) {
+      const int tn = 64 / (tw * th);
+      if ((tn > 1 && (tw < Wo || th < Ho)) || tn > 64) continue;      // several images per box only for whole (padded) images
+      const double tiles = (double)esb_div_up(Wo, tw) * esb_div_up(Ho, th) * esb_div_up(n_img, tn);
+      const double eff = (double)Wo * Ho * n_img / (tiles * 64.0) + 1e-6 * tw;
+      if (eff > best) { best = eff; g.TW = tw; g.TH = th; g.TN = tn; }
+    }
+  g.tiles_w = esb_div_up(Wo, g.TW); g.tiles_h = esb_div_up(Ho, g.TH); g.tiles_n = esb_div_up(n_img, g.TN);
+  const int n_tile = cout >= 128 ? 128 : cout;
+  const int n_blocks = cout / n_tile;
+  const int slices = esb_div_up(kh * kw * g.chunks_per_tap, g.atoms_per_slice);
+  CUtensorMap tmx, tmdy;
+  {
+    unsigned long long dims[4] = {(unsigned long long)cin, (unsigned long long)W, (unsigned long long)H, (unsigned long long)n_img};
+    unsigned long long str[3] = {(unsigned long long)cin * 2, (unsigned long long)W * cin * 2, (unsigned long long)H * W * cin * 2};
+    unsigned box[4] = {(unsigned)g.aw, (unsigned)((g.TW - 1) * stride + 1), (unsigned)((g.TH - 1) * stride + 1), (unsigned)g.TN};
+    unsigned es[4] = {1, (unsigned)stride, (unsigned)stride, 1};
+    int rc = esb_tma_encode(&tmx, x, 4, dims, str, box, es, g.aw * 2);
+    if (rc != ESB_OK) return rc;
+  }
+  {
+    const int na = n_tile < 64 ? n_tile : 64;
+    unsigned long long dims[4] = {(unsigned long long)cout, (unsigned long long)Wo, (unsigned long long)Ho, (unsigned long long)n_img};
+    unsigned long long str[3] = {(unsigned long long)cout * 2, (unsigned long long)Wo * cout * 2, (unsigned long long)Ho * Wo * cout * 2};
+    unsigned box[4] = {(unsigned)na, (unsigned)g.TW, (unsigned)g.TH, (unsigned)g.TN};
+    int rc = esb_tma_encode(&tmdy, dy, 4, dims, str, box, nullptr, na * 2);
+    if (rc != ESB_OK) return rc;
+  }
+  int rc;
+  switch (n_tile) {
+    case 16: rc = launch_wgrad_tma<16>(tmx, tmdy, dw_t, g, slices, n_blocks, (cudaStream_t)stream_); break;
+    case 32: rc = launch_wgrad_tma<32>(tmx, tmdy, dw_t, g, slices, n_blocks, (cudaStream_t)stream_); break;
+    case 64: rc = launch_wgrad_tma<64>(tmx, tmdy, dw_t, g, slices, n_blocks, (cudaStream_t)stream_); break;
+    case 128: rc = launch_wgrad_tma<128>(tmx, tmdy, dw_t, g, slices, n_blocks, (cudaStream_t)stream_); break;
+    default: esb_set_error("esb_conv2d_tma_wgrad: unsupported Cout %d", cout); return ESB_EINVAL;
+  }
+  if (rc != ESB_OK) return rc;
+  ESB_CUDA_LAUNCH_CHECK("conv_tma_wgrad_kernel");
   return ESB_OK;
 }

@@ -229,6 +229,57 @@ extern "C" int esb_hash_lookup(const int* query, long long nq, const unsigned lo
 }
 
 // ------------------------------------------------------------------------------------------------
+// ME `features_at_coordinates` (†upstream; used by FCAF3D `_prune`, fcaf3d_head.py:1091-1114): multilinear interpolation of
+// the rows of a stride-`ts` tensor at integer query coordinates [b,x,y,z]; absent lattice points contribute 0. Arithmetic is
+// spelled out operation by operation (no FMA contraction) in the order of the torch expression the oracle uses:
+//   frac = q/ts - floor(q/ts); w_k = ((wx*wy)*wz); out = sum_{k=0..7} F[idx_k] * w_k  (k = dx + 2dy + 4dz).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void interp_features_kernel(const int* __restrict__ q, long long nq, const unsigned long long* __restrict__ keys,
+                                       const int* __restrict__ vals, uint32_t mask, const T* __restrict__ feats, int C, int ts,
+                                       float inv_ts, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const int4 c = reinterpret_cast<const int4*>(q)[i];
+  float frac[3];
+  int base[3];
+  const int xyz[3] = {c.y, c.z, c.w};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float v = __fmul_rn((float)xyz[a], inv_ts);      // ts is a power of two: exact, = q / ts
+    const float fl = floorf(v);
+    frac[a] = __fsub_rn(v, fl);
+    base[a] = (int)fl * ts;
+  }
+  for (int ch = 0; ch < C; ++ch) out[i * C + ch] = 0.f;
+  for (int k = 0; k < 8; ++k) {
+    const int d[3] = {k & 1, (k >> 1) & 1, (k >> 2) & 1};
+    float w = d[0] ? frac[0] : __fsub_rn(1.f, frac[0]);
+    w = __fmul_rn(w, d[1] ? frac[1] : __fsub_rn(1.f, frac[1]));
+    w = __fmul_rn(w, d[2] ? frac[2] : __fsub_rn(1.f, frac[2]));
+    const int x = base[0] + d[0] * ts, y = base[1] + d[1] * ts, z = base[2] + d[2] * ts;
+    const int idx = esb_coord_in_range(c.x, x, y, z) ? esb_hash_find(keys, vals, mask, esb_pack_key(c.x, x, y, z)) : -1;
+    if (idx >= 0)
+      for (int ch = 0; ch < C; ++ch)
+        out[i * C + ch] = __fadd_rn(out[i * C + ch], __fmul_rn(esb_to_float(feats[(long long)idx * C + ch]), w));
+  }
+}
+
+extern "C" int esb_interp_features(const int* query, long long nq, const unsigned long long* keys, const int* vals,
+                                   long long cap, const void* feats, int C, int ts, int dtype, float* out, void* stream) {
+  ESB_CHECK_ARG(ts >= 1 && (ts & (ts - 1)) == 0 && C >= 1, "esb_interp_features: tensor stride must be a power of two");
+  if (nq == 0) return ESB_OK;
+  if (dtype == ESB_F32)
+    interp_features_kernel<float><<<esb_div_up(nq, 256), 256, 0, (cudaStream_t)stream>>>(
+        query, nq, keys, vals, (uint32_t)(cap - 1), (const float*)feats, C, ts, 1.0f / (float)ts, out);
+  else
+    interp_features_kernel<__nv_bfloat16><<<esb_div_up(nq, 256), 256, 0, (cudaStream_t)stream>>>(
+        query, nq, keys, vals, (uint32_t)(cap - 1), (const __nv_bfloat16*)feats, C, ts, 1.0f / (float)ts, out);
+  ESB_CUDA_LAUNCH_CHECK("interp_features_kernel");
+  return ESB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel map: nbr[k*n_out + o] = row of (out_coord[o] + offset[k]) in the input table, or -1.
 // Output-stationary layout: offset-major so a warp's stores along o coalesce.
 // ------------------------------------------------------------------------------------------------

@@ -694,6 +694,13 @@ class SparseTensor:
         cm = self.cmap
         cm.ensure_table()
         ts = cm.stride
+        if (query.is_cuda and self.F.dtype in (torch.float32, torch.bfloat16) and ts & (ts - 1) == 0
+                and (not query.is_floating_point() or bool(getattr(query, '_esb_integer', False)))):
+            qi = query.to(torch.int32).contiguous()            # integer lattice queries (child coordinates): one kernel
+            out = torch.empty((qi.shape[0], self.F.shape[1]), dtype=torch.float32, device=qi.device)
+            call('esb_interp_features', ptr(qi), qi.shape[0], ptr(cm.keys), ptr(cm.vals), cm.cap, ptr(self.F.contiguous()),
+                 self.F.shape[1], ts, _ffi.dtype_code(self.F.dtype), ptr(out), stream())
+            return out
         q = query.float()
         b = q[:, 0].to(torch.int32)
         base = torch.floor(q[:, 1:] / ts)

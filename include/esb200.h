@@ -44,6 +44,10 @@ int esb_coord_unique(const int* coords_in, long long n, int div, unsigned long l
 int esb_hash_build(const int* coords, long long n, unsigned long long* keys, int* vals, long long cap, void* stream);
 int esb_hash_lookup(const int* query, long long nq, const unsigned long long* keys, const int* vals, long long cap,
                     int* out, void* stream);
+/* ME `features_at_coordinates` at integer query coordinates (fcaf3d_head.py:1091-1114 `_prune`): multilinear interpolation of
+ * the rows of the stride-`ts` tensor whose hash table is (keys, vals); out (nq, C) fp32; absent lattice points contribute 0. */
+int esb_interp_features(const int* query, long long nq, const unsigned long long* keys, const int* vals, long long cap,
+                        const void* feats, int C, int ts, int dtype, float* out, void* stream);
 int esb_kernel_map(const int* out_coords, long long n_out, const int* offsets_host, int K,
                    const unsigned long long* keys, const int* vals, long long cap, int* nbr, void* stream);
 int esb_kernel_map_transpose(const int* nbr_out, int K, long long n_out, long long n_in, int* nbr_in, void* stream);
@@ -124,10 +128,15 @@ int esb_spconv_tma_wgrad(const void* x, const void* dy, const int* pair_in, cons
  * cin, cout in {16, 32, 64, 128, 256, 512, ...}. */
 int esb_conv2d_tma_fwd(const void* x, const void* w_ohwi, const float* bias, const void* residual, void* y, int n_img,
                        int H, int W, int cin, int cout, int kh, int kw, int stride, int pad, int relu, void* stream);
-/* Input gradient of a stride-1 convolution with the same kernel: dx (n_img,H,W,cin) from dy (n_img,Ho,Wo,cout) and the
- * forward filter as stored (taps visited in reverse, filter read as the MN-major B operand: no transposed copy). */
+/* Weight gradient, TMA-fed (pixels = reduction dimension, both operands arrive as [pixel][channel] boxes = MN-major tcgen05
+ * operands): dw_t (kh*kw*cin, cout) fp32, ZEROED BY THE CALLER, dW[co,ci,ky,kx] = dw_t[(ky*kw+kx)*cin+ci, co]. */
+int esb_conv2d_tma_wgrad(const void* x, const void* dy, float* dw_t, int n_img, int H, int W, int cin, int cout, int kh,
+                         int kw, int stride, int pad, void* stream);
+/* Input gradient (stride 1 or 2) with the same kernel: dx (n_img,H,W,cin) from dy (n_img,Ho,Wo,cout) and the forward filter as
+ * stored (filter read as the MN-major B operand: no transposed copy). Stride 1: flipped taps. Stride 2: one launch per parity
+ * class of dx, stored through a tensor map that skips every other pixel; every dx element is written exactly once. */
 int esb_conv2d_tma_dgrad(const void* dy, const void* w_ohwi, void* dx, int n_img, int H, int W, int cin, int cout, int kh,
-                         int kw, int pad, void* stream);
+                         int kw, int stride, int pad, void* stream);
 /* The 7x7/2 stem on the 3-channel image as a tcgen05 implicit GEMM with the im2col rows built in shared memory
  * (csrc/conv_tma.cu::stem7x7_tc_kernel). x (n_img,H,W,3) bf16 NHWC, w_ohwi (16,7,7,3) bf16, bias (16) fp32, y (n_img,Ho,Wo,16). */
 int esb_stem7x7_tc(const void* x, const void* w_ohwi, const float* bias, void* y, int n_img, int H, int W, int relu,

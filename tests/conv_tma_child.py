@@ -78,13 +78,25 @@ def run_case(case, dev):
     tol = 1e-2 * max(float(ref.abs().max()), 1.0)            # bf16 output rounding of values up to |max|
     print(json.dumps(dict(kind='fwd', case=list(case[:5]) + [list(hw), n, with_res], err=err, tol=tol,
                           ok=bool(out.shape == ref.shape and err <= tol))), flush=True)
-    if stride != 1:
+    # weight gradient (TMA-fed, pixels are the reduction dimension)
+    from embodiedscan_b200.backbones import conv2d_tma_wgrad
+    wr = w.float().requires_grad_(True)
+    yw = F.conv2d(x.float(), wr, None, stride, pad)
+    dyw = torch.randn(yw.shape, generator=g).bfloat16()
+    yw.backward(dyw.float())
+    dw = conv2d_tma_wgrad(xd, dyw.to(dev).contiguous(memory_format=torch.channels_last), tuple(w.shape), stride, pad)
+    torch.cuda.synchronize()
+    err = float((dw.float().cpu() - wr.grad).abs().max())
+    tol = 1e-2 * max(float(wr.grad.abs().max()), 1.0)
+    print(json.dumps(dict(kind='wgrad', case=list(case[:5]) + [list(hw), n], err=err, tol=tol,
+                          ok=bool(tuple(dw.shape) == tuple(wr.grad.shape) and err <= tol))), flush=True)
+    if stride not in (1, 2):
         return
     xr = x.float().requires_grad_(True)
     yr = F.conv2d(xr, w.float(), None, stride, pad)
     dy = torch.randn(yr.shape, generator=g).bfloat16()
     yr.backward(dy.float())
-    dx = conv2d_tma_dgrad(dy.to(dev).contiguous(memory_format=torch.channels_last), wd, hw, pad)
+    dx = conv2d_tma_dgrad(dy.to(dev).contiguous(memory_format=torch.channels_last), wd, hw, pad, stride)
     torch.cuda.synchronize()
     err = float((dx.float().cpu() - xr.grad).abs().max())
     tol = 1e-2 * max(float(xr.grad.abs().max()), 1.0)
@@ -122,8 +134,23 @@ def bench(dev, n=80):
             torch.cuda.synchronize()
             ms[name] = e0.elapsed_time(e1) / 10
         byt = (x.numel() + y.numel() + w.numel()) * 2
+        from embodiedscan_b200.backbones import conv2d_tc_wgrad, conv2d_tma_wgrad
+        dyb = torch.randn_like(y)
+        for name, fn in (('wgrad_tma', lambda: conv2d_tma_wgrad(x, dyb, tuple(w.shape), stride, pad)),
+                         ('wgrad_tc', lambda: conv2d_tc_wgrad(x, dyb, tuple(w.shape), stride, pad))):
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms[name] = e0.elapsed_time(e1) / 5
         print(json.dumps(dict(kind='bench', case=[cin, cout, k, stride, pad, list(hw), n], us_tma=1e3 * ms['tma'],
-                              us_cudnn=1e3 * ms['cudnn'], gbs_tma=byt / ms['tma'] / 1e6, mbytes=byt / 1e6)), flush=True)
+                              us_cudnn=1e3 * ms['cudnn'], gbs_tma=byt / ms['tma'] / 1e6, mbytes=byt / 1e6,
+                              us_wgrad_tma=1e3 * ms['wgrad_tma'], us_wgrad_tc=1e3 * ms['wgrad_tc'],
+                              gbs_wgrad_tma=byt / ms['wgrad_tma'] / 1e6)), flush=True)
 
 
 def main():
