@@ -18,6 +18,7 @@
 //
 // Roofline: pair model bytes = P*(Cin+Cout)*2 + 8P + K*Cin*Cout*2; the gather is L2-fed.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 using namespace esb_tc;
 
@@ -43,92 +44,98 @@ __global__ void tile_mask_kernel(const int* __restrict__ nbr, int K, int n, uint
 // ------------------------------------------------------------------------------------------------------------
 // B_MN = false: wt is (K, cout, cin)  (W_k^T, reduction dim contiguous  -> K-major B; used by dgrad with wt = W itself)
 // B_MN = true : wt is (K, cin, cout)  (W_k as stored, output dim contiguous -> MN-major B; used by forward, no transpose)
-template <int N_TILE, int STAGES, bool B_MN>
-__global__ void __launch_bounds__(160)
-spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wt,
+// MT = 128-row tiles per CTA: with MT = 2 one filter stage feeds two accumulators (half the filter traffic per output row:
+// at C = 64 the filter re-reads were as large as the gather itself) and 256 producer threads gather, one tile each.
+// The filter tile of every stage is ONE tiled TMA box (cp.async.bulk.tensor) issued by thread 0 — the 128B-swizzled layouts
+// tcgen05 wants are what the tensor map writes; the gather stays on cp.async (tile::gather4 was measured 3x slower, see
+// spconv_tma.cu).
+template <int N_TILE, int STAGES, bool B_MN, int MT>
+__global__ void __launch_bounds__(MT * 128 + 32)
+spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__ CUtensorMap tmw,
                      const int* __restrict__ nbr, const uint32_t* __restrict__ masks, __nv_bfloat16* __restrict__ y,
                      int n_out, int cin, int cout, int K) {
+  constexpr int A_BYTES = MT * A_STAGE_BYTES;
   constexpr int B_STAGE_BYTES = N_TILE * 128;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   constexpr int LAG = STAGES - 2;                 // stages kept in flight per producer thread before it signals
+  constexpr int NPROD = MT * 128;
+  constexpr int TMEM_COLS = MT * N_TILE < 32 ? 32 : MT * N_TILE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
-  __shared__ int idx_s[2][TC_M];
+  __shared__ int idx_s[2][NPROD];
 
   const int warp = threadIdx.x >> 5;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x;                     // MT * 128 output rows
   const int n0 = blockIdx.y * N_TILE;
-  const uint32_t mask = masks[tile];
+  uint32_t mask = masks[tile * MT];
+  if (MT == 2 && (tile * 2 + 1) * TC_M < n_out) mask |= masks[tile * 2 + 1];
   const int nchunk = cin / TC_BK;
   const int total = __popc(mask) * nchunk;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 128);
+      mbar_init(&full_bar[s], NPROD + 1);          // every producer thread + the expect_tx arrival of the filter box
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmw);
   }
-  if (warp == 4) tmem_alloc(tmem_slot, N_TILE < 32 ? 32 : N_TILE);
+  if (warp == NPROD / 32) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < NPROD / 32) {
     // ---------------- producers ----------------
     // Lane mapping: 8 consecutive lanes fetch the 8 x 16 B chunks of ONE gathered row, so a warp-wide cp.async touches
     // 4 rows x 128 B (4 L1 wavefronts) instead of 32 different rows (32 wavefronts: the round-1a L1TEX bottleneck).
-    // Thread t owns chunk (t & 7) of rows (t >> 3) + 16 i, i = 0..7; r & 7 == (t >> 3) & 7 for all of them.
+    // Thread t of tile m = t >> 7 owns chunk (t & 7) of rows ((t & 127) >> 3) + 16 i, i = 0..7.
     const int t = threadIdx.x;
-    const int sub = t & 7, rgrp = t >> 3;
+    const int tm = t >> 7, tl = t & 127;
+    const int sub = tl & 7, rgrp = tl >> 3;
     const uint32_t sw = (uint32_t)(rgrp & 7);
-    const uint32_t a_thread_off = (uint32_t)((rgrp >> 3) * 1024 + (rgrp & 7) * 128) + ((sub ^ sw) << 4);
+    const uint32_t a_thread_off = (uint32_t)(tm * A_STAGE_BYTES + (rgrp >> 3) * 1024 + (rgrp & 7) * 128) + ((sub ^ sw) << 4);
     int it = 0, kcount = 0;
-    const int my_row = tile * TC_M + t;
+    const int my_row = tile * MT * TC_M + t;
     // the neighbour index of the NEXT offset is loaded while the stages of the current one are in flight
     int v_next = (mask && my_row < n_out) ? nbr[(long long)(__ffs(mask) - 1) * n_out + my_row] : -1;
     for (uint32_t mk = mask; mk; mk &= mk - 1, ++kcount) {
       const int k = __ffs(mk) - 1;
       int* idx_buf = idx_s[kcount & 1];
       idx_buf[t] = v_next;
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // producers only (warps 0-3)
+      asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");     // producers only
       {
         const uint32_t rest = mk & (mk - 1);
         v_next = (rest && my_row < n_out) ? nbr[(long long)(__ffs(rest) - 1) * n_out + my_row] : -1;
       }
       int src[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) src[i] = idx_buf[rgrp + 16 * i];
-      const __nv_bfloat16* wk = B_MN ? wt + (long long)k * cin * cout + n0 : wt + ((long long)k * cout + n0) * cin;
+      for (int i = 0; i < 8; ++i) src[i] = idx_buf[tm * 128 + rgrp + 16 * i];
       for (int c = 0; c < nchunk; ++c, ++it) {
         const int s = it % STAGES;
         if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES) + a_thread_off;
+        const uint32_t stage_base = smem_u32(smem + s * STAGE_BYTES);
+        if (t == 0) {        // the filter tile of this stage: one (B_MN: N_TILE / 64) tiled TMA box(es)
+          mbar_expect_tx(&full_bar[s], B_STAGE_BYTES);
+          const uint32_t b_base = stage_base + A_BYTES;
+          if (B_MN) {        // stored kernel (K*cin rows, cout columns): 64 reduction rows x 64 columns per box
+#pragma unroll
+            for (int a = 0; a < N_TILE / 64; ++a) tma_load_2d(&tmw, &full_bar[s], b_base + a * 8192, n0 + a * 64, k * cin + c * TC_BK);
+          } else {           // (K*cout rows, cin columns): N_TILE output rows x 64 reduction columns
+            tma_load_2d(&tmw, &full_bar[s], b_base, c * TC_BK, k * cout + n0);
+          }
+        }
+        const uint32_t a_base = stage_base + a_thread_off;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           cp_async16_ca(a_base + i * 2048, x + (long long)(src[i] >= 0 ? src[i] : 0) * cin + c * TC_BK + sub * 8,
                         src[i] >= 0 ? 16 : 0);
-        const uint32_t b_base = smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES);
-        const int r = t;
-#pragma unroll
-        for (int q = 0; q < N_TILE / 16; ++q) {
-          const int idx = q * 128 + r;
-          if (B_MN) {   // 64 reduction rows (cin) x N_TILE/8 chunks along cout; canonical MN-major SW128 atoms
-            const int kk = idx / (N_TILE / 8), nc = idx % (N_TILE / 8);
-            cp_async16_cg(b_base + (nc >> 3) * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + (((nc & 7) ^ (kk & 7)) << 4),
-                          wk + (long long)(c * TC_BK + kk) * cout + nc * 8, 16);
-          } else {
-            const int n = idx >> 3, j = idx & 7;
-            cp_async16_cg(b_base + (n >> 3) * 1024 + (n & 7) * 128 + ((j ^ (n & 7)) << 4),
-                          wk + (long long)n * cin + c * TC_BK + j * 8, 16);
-          }
-        }
         cp_async_commit();
         if (it >= LAG) {
           cp_async_wait<LAG>();
@@ -143,7 +150,7 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     for (int d = (total > LAG ? total - LAG : 0); d < total; ++d) mbar_arrive(&full_bar[d % STAGES]);
 
     // ---------------- epilogue ----------------
-    const int row = tile * TC_M + threadIdx.x;       // TMEM lane = tile row
+    const int row = tile * MT * TC_M + t;            // TMEM lane = row within its 128-row tile; accumulator = tile tm
     if (total > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
@@ -153,7 +160,7 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
       uint32_t v[32];
       if (total > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tm * N_TILE + c0), v);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0u;
@@ -172,7 +179,7 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     }
     tc_fence_before();
   } else {
-    // ---------------- MMA issuer (warp 4) ----------------
+    // ---------------- MMA issuer (last warp) ----------------
     const uint32_t idesc = make_idesc(TC_M, N_TILE, 0, B_MN ? 1 : 0);
     for (int it = 0; it < total; ++it) {
       const int s = it % STAGES;
@@ -180,12 +187,14 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
       tc_fence_after();
       if ((threadIdx.x & 31) == 0) {
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+        const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < TC_BK / 16; ++kk) {
-          uint64_t ad = make_desc(a_addr + kk * 32, 16, 1024);
-          uint64_t bd = B_MN ? make_desc(b_addr + kk * 2048, 8192, 1024) : make_desc(b_addr + kk * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          const uint64_t bd = B_MN ? make_desc(b_addr + kk * 2048, 8192, 1024) : make_desc(b_addr + kk * 32, 16, 1024);
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            umma_bf16(tmem_base + m * N_TILE, make_desc(a_addr + m * A_STAGE_BYTES + kk * 32, 16, 1024), bd, idesc,
+                      (it > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
         if (it == total - 1) umma_commit(accum_bar);
@@ -195,9 +204,9 @@ spconv_tc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NPROD / 32) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, N_TILE < 32 ? 32 : N_TILE);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -375,16 +384,16 @@ spconv_tc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   (void)NB_ATOMS;
 }
 
-template <int N_TILE, int STAGES, bool B_MN>
-int launch_fwd(const void* x, const void* wt, const int* nbr, const unsigned* masks, void* y, long long n_out, int cin,
+template <int N_TILE, int STAGES, bool B_MN, int MT>
+int launch_fwd(const void* x, const CUtensorMap& tmw, const int* nbr, const unsigned* masks, void* y, long long n_out, int cin,
                int cout, int K, cudaStream_t stream) {
-  size_t smem = (size_t)STAGES * (A_STAGE_BYTES + N_TILE * 128) + 1024 + 256;
-  auto kern = spconv_tc_fwd_kernel<N_TILE, STAGES, B_MN>;
+  size_t smem = (size_t)STAGES * (MT * A_STAGE_BYTES + N_TILE * 128) + 1024 + 256;
+  auto kern = spconv_tc_fwd_kernel<N_TILE, STAGES, B_MN, MT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { esb_set_error("spconv_tc_fwd: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
-  dim3 grid(esb_div_up(n_out, TC_M), cout / N_TILE);
-  kern<<<grid, 160, smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)wt, nbr, masks, (__nv_bfloat16*)y,
-                                    (int)n_out, cin, cout, K);
+  dim3 grid(esb_div_up(n_out, MT * TC_M), cout / N_TILE);
+  kern<<<grid, MT * 128 + 32, smem, stream>>>((const __nv_bfloat16*)x, tmw, nbr, masks, (__nv_bfloat16*)y, (int)n_out, cin,
+                                              cout, K);
   return ESB_OK;
 }
 
@@ -425,15 +434,33 @@ extern "C" int esb_spconv_tc_fwd(const void* x, const void* wt, const int* nbr, 
   int rc;
   // wide tiles amortise the gather; narrow tiles when there are too few row tiles to fill 148 SMs
   long long row_tiles = (n_out + TC_M - 1) / TC_M;
-#define ESB_TC_LAUNCH(NT, ST)                                                                         \
-  (w_layout ? launch_fwd<NT, ST, true>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream)             \
-            : launch_fwd<NT, ST, false>(x, wt, nbr, masks, y, n_out, cin, cout, K, stream))
-  if (cout % 256 == 0 && row_tiles * (cout / 256) >= 148)
-    rc = ESB_TC_LAUNCH(256, 4);
-  else if (cout % 128 == 0 && row_tiles * (cout / 128) >= 148)
-    rc = ESB_TC_LAUNCH(128, 3);
+  const int n_tile = (cout % 256 == 0 && row_tiles * (cout / 256) >= 148) ? 256
+                     : (cout % 128 == 0 && row_tiles * (cout / 128) >= 148) ? 128 : 64;
+  // two row tiles per CTA (one filter stage, two accumulators) while the grid still covers the SMs twice over
+  const bool two = n_tile <= 128 && (row_tiles / 2) * (cout / n_tile) >= 2 * 148 && getenv("ESB200_SPCONV_MT1") == nullptr;
+  CUtensorMap tmw;
+  {
+    unsigned long long dims[2], str[1];
+    unsigned box[2];
+    if (w_layout) {   // (K*cin rows, cout columns): 64 x 64 boxes
+      dims[0] = (unsigned long long)cout; dims[1] = (unsigned long long)K * cin; str[0] = (unsigned long long)cout * 2;
+      box[0] = 64; box[1] = 64;
+    } else {          // (K*cout rows, cin columns): N_TILE rows x 64 columns
+      dims[0] = (unsigned long long)cin; dims[1] = (unsigned long long)K * cout; str[0] = (unsigned long long)cin * 2;
+      box[0] = 64; box[1] = (unsigned)n_tile;
+    }
+    rc = esb_tma_encode(&tmw, wt, 2, dims, str, box, nullptr, 128);
+    if (rc != ESB_OK) return rc;
+  }
+#define ESB_TC_LAUNCH(NT, ST, MTV)                                                                       \
+  (w_layout ? launch_fwd<NT, ST, true, MTV>(x, tmw, nbr, masks, y, n_out, cin, cout, K, stream)         \
+            : launch_fwd<NT, ST, false, MTV>(x, tmw, nbr, masks, y, n_out, cin, cout, K, stream))
+  if (n_tile == 256)
+    rc = ESB_TC_LAUNCH(256, 4, 1);
+  else if (n_tile == 128)
+    rc = two ? ESB_TC_LAUNCH(128, 4, 2) : ESB_TC_LAUNCH(128, 3, 1);
   else
-    rc = ESB_TC_LAUNCH(64, 4);
+    rc = two ? ESB_TC_LAUNCH(64, 4, 2) : ESB_TC_LAUNCH(64, 4, 1);
 #undef ESB_TC_LAUNCH
   if (rc != ESB_OK) return rc;
   ESB_CUDA_LAUNCH_CHECK("spconv_tc_fwd_kernel");

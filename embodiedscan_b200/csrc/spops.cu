@@ -349,6 +349,93 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y
   }
 }
 
+// ---------------- fused BatchNorm statistics (one segment, bf16 rows) ----------------
+// ONE pass over x: sum and sum of squares of v = x - pivot (pivot = row 0 of the column: keeps E[v^2] - E[v]^2 free of the
+// catastrophic cancellation a raw single-pass variance has when |mean| >> std), accumulated per block in shared memory and
+// added to stats[0] (sum v), stats[1] (sum v^2). The apply kernel turns them into mean / rstd on the fly.
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ x, long long N, int C, int rows_per_block, float* __restrict__ stats) {
+  extern __shared__ float sh[];                    // [2][C]
+  float* s_sum = sh;
+  float* s_sq = sh + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int tpr = C / 8;                           // threads per row (16-byte pieces)
+  const int c = (threadIdx.x % tpr) * 8;
+  const int rsub = threadIdx.x / tpr, rstep = blockDim.x / tpr;
+  const long long r_beg = (long long)blockIdx.x * rows_per_block;
+  const long long r_end = r_beg + rows_per_block < N ? r_beg + rows_per_block : N;
+  float piv[8], sum[8], sq[8];
+  load8<T>(x + c, piv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sum[e] = sq[e] = 0.f;
+  if (rsub < rstep) {
+    for (long long r = r_beg + rsub; r < r_end; r += rstep) {
+      float v[8];
+      load8<T>(x + r * C + c, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[e] - piv[e];
+        sum[e] += d;
+        sq[e] = fmaf(d, d, sq[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&s_sum[c + e], sum[e]);
+      atomicAdd(&s_sq[c + e], sq[e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&stats[i], s_sum[i]);
+    atomicAdd(&stats[C + i], s_sq[i]);
+  }
+}
+
+// y = act((x - mean) * rstd * gamma + beta + res) with mean / rstd derived from the raw sums of bn_stats_kernel; block 0 also
+// publishes mean -> stats[2], rstd -> stats[3] (what the backward pass reads) and updates the running statistics.
+template <typename T>
+__global__ void bn_apply_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, long long N, int C,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, int act,
+                                      float* __restrict__ stats, T* __restrict__ y) {
+  const float inv_n = 1.f / (float)N;
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      const float m = stats[i] * inv_n;
+      const float var = fmaxf(stats[C + i] * inv_n - m * m, 0.f);
+      const float mean = esb_to_float<T>(x[i]) + m;
+      stats[2 * C + i] = mean;
+      stats[3 * C + i] = rsqrtf(var + eps);
+      if (running_mean != nullptr) {
+        const float unbiased = N > 1 ? var * (float)N / (float)(N - 1) : var;
+        running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * mean;
+        running_var[i] = (1.f - momentum) * running_var[i] + momentum * unbiased;
+      }
+    }
+  }
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cv = C / 8;
+  if (t >= N * cv) return;
+  const long long r = t / cv;
+  const int c = (int)(t - r * cv) * 8;
+  float v[8], piv[8], rs[8];
+  load8<T>(x + r * C + c, v);
+  load8<T>(x + c, piv);
+  if (res != nullptr) load8<T>(res + r * C + c, rs);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float m = stats[c + e] * inv_n;
+    const float var = fmaxf(stats[C + c + e] * inv_n - m * m, 0.f);
+    const float g = gamma ? gamma[c + e] : 1.f, b = beta ? beta[c + e] : 0.f;
+    float z = (v[e] - (piv[e] + m)) * rsqrtf(var + eps) * g + b;
+    if (res != nullptr) z += rs[e];
+    v[e] = act_fwd(z, act);
+  }
+  store8<T>(y + r * C + c, v);
+}
+
 // out[r, :] = a[ia(r), :] + b[ib[r], :] with ia(r) = ia ? ia[r] : (r < na ? r : -1); a negative index contributes zeros.
 // One thread per (row, 8-channel piece): the row gather of unions (A + B on different coordinate maps), of their gradients
 // and of every `x[idx]` on the path; each output element is written once (no atomics).
@@ -520,5 +607,28 @@ extern "C" int esb_gather2_rows(const void* a, const int* ia, long long na, cons
   DISPATCH_T(dtype, (gather2_rows_kernel<T><<<esb_div_up(n_vec, 256), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)a, ia, na, (const T*)b, ib, (T*)out, n_vec, C)));
   ESB_CUDA_LAUNCH_CHECK("gather2_rows_kernel");
+  return ESB_OK;
+}
+
+// BatchNorm (one segment) forward in TWO launches: one statistics pass + one apply pass (esb_norm_fwd takes five: two
+// centred passes with their finalisation kernels, the parity arithmetic). stats (4, C) fp32: [sum v, sum v^2, mean, rstd];
+// rows 2 and 3 are the saved tensors of the backward pass. x / res / y (N, C), C % 8 == 0, 16 <= C <= 2048.
+extern "C" int esb_batchnorm_fwd_fused(const void* x, const void* res, long long N, int C, const float* gamma, const float* beta,
+                                       float eps, float* running_mean, float* running_var, float momentum, int act, float* stats,
+                                       void* y, int dtype, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESB_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048, "esb_batchnorm_fwd_fused: C must be a multiple of 8 in [8, 2048]");
+  ESB_CUDA_CALL(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, stream));
+  if (N == 0) return ESB_OK;
+  long long rpb = (N + 295) / 296;
+  if (rpb < 64) rpb = 64;
+  const int grid_a = esb_div_up(N, rpb);
+  const long long n_vec = N * (C / 8);
+  DISPATCH_T(dtype, (bn_stats_kernel<T><<<grid_a, 256, 2 * C * sizeof(float), stream>>>((const T*)x, N, C, (int)rpb, stats)));
+  ESB_CUDA_LAUNCH_CHECK("bn_stats_kernel");
+  DISPATCH_T(dtype, (bn_apply_fused_kernel<T><<<esb_div_up(n_vec, 256), 256, 0, stream>>>(
+                        (const T*)x, (const T*)res, N, C, gamma, beta, eps, running_mean, running_var, momentum, act, stats,
+                        (T*)y)));
+  ESB_CUDA_LAUNCH_CHECK("bn_apply_fused_kernel");
   return ESB_OK;
 }

@@ -505,17 +505,24 @@ class _SegNorm(torch.autograd.Function):
         x = x.contiguous()
         N, C = x.shape
         dev = x.device
-        mean = torch.empty((S, C), dtype=torch.float32, device=dev)
-        rstd = torch.empty((S, C), dtype=torch.float32, device=dev)
         y = torch.empty_like(x)
         g = gamma.detach() if gamma is not None else None      # fp32 contiguous parameters: used as is
         b = beta.detach() if beta is not None else None
         assert (g is None or (g.dtype == torch.float32 and g.is_contiguous())) and \
             (b is None or (b.dtype == torch.float32 and b.is_contiguous()))
         resc = res.contiguous() if res is not None else None
-        call('esb_norm_fwd', ptr(x), ptr(resc), ptr(seg_off), ptr(row_seg), S, N, max_rows, C, ptr(g), ptr(b), eps,
-             ptr(running_mean), ptr(running_var), momentum, act, ptr(mean), ptr(rstd), ptr(y), _ffi.dtype_code(x.dtype),
-             stream())
+        if S == 1 and x.dtype == torch.bfloat16 and C % 8 == 0 and 8 <= C <= 2048 and N > 0:
+            # BatchNorm on the throughput path: one shifted single-pass statistics kernel + one apply kernel
+            stats = torch.empty((4, C), dtype=torch.float32, device=dev)
+            call('esb_batchnorm_fwd_fused', ptr(x), ptr(resc), N, C, ptr(g), ptr(b), eps, ptr(running_mean), ptr(running_var),
+                 momentum, act, ptr(stats), ptr(y), _ffi.dtype_code(x.dtype), stream())
+            mean, rstd = stats[2:3], stats[3:4]
+        else:
+            mean = torch.empty((S, C), dtype=torch.float32, device=dev)
+            rstd = torch.empty((S, C), dtype=torch.float32, device=dev)
+            call('esb_norm_fwd', ptr(x), ptr(resc), ptr(seg_off), ptr(row_seg), S, N, max_rows, C, ptr(g), ptr(b), eps,
+                 ptr(running_mean), ptr(running_var), momentum, act, ptr(mean), ptr(rstd), ptr(y), _ffi.dtype_code(x.dtype),
+                 stream())
         ctx.save_for_backward(x, y, mean, rstd, g, seg_off, row_seg)   # None entries are allowed
         ctx.meta = (S, max_rows, act, res is not None, gamma.shape if gamma is not None else None,
                     beta.shape if beta is not None else None)

@@ -79,6 +79,11 @@ int esb_norm_fwd(const void* x, const void* res, const int* seg_off, const int* 
                  int max_seg_rows, int C, const float* gamma, const float* beta, float eps, float* running_mean,
                  float* running_var, float momentum, int act, float* mean, float* rstd, void* y, int dtype,
                  void* stream);
+/* BatchNorm (one segment) forward in two launches: one shifted single-pass statistics kernel + one apply kernel that derives
+ * mean / rstd on the fly. stats (4,C) fp32 = [sum v, sum v^2, mean, rstd]; rows 2, 3 are what esb_norm_bwd takes as mean / rstd. */
+int esb_batchnorm_fwd_fused(const void* x, const void* res, long long N, int C, const float* gamma, const float* beta, float eps,
+                            float* running_mean, float* running_var, float momentum, int act, float* stats, void* y, int dtype,
+                            void* stream);
 int esb_norm_apply(const void* x, const void* res, const int* row_seg, long long N, int C, const float* mean,
                    const float* rstd, const float* gamma, const float* beta, int act, void* y, int dtype, void* stream);
 int esb_norm_bwd(const void* x, const void* y, const void* dy, const int* seg_off, const int* row_seg, int S,

@@ -614,3 +614,31 @@ def test_rows_gemm_tc_matches_matmul():
         _close(y, yr, 2e-2, 'rows_gemm fwd')
         _close(x.grad, xr.grad, 2e-2, 'rows_gemm dgrad')
         _close(w.grad, wr.grad, 2e-2, 'rows_gemm wgrad')
+
+
+def test_fused_batchnorm_bf16_matches_reference():
+    """esb_batchnorm_fwd_fused (shifted single-pass statistics + on-the-fly apply) against nn.BatchNorm1d in fp32 on the
+    bf16-rounded rows, with a large mean/std ratio (what a naive single-pass variance gets wrong), residual + ELU, backward."""
+    from embodiedscan_b200 import sparse as SP
+    torch.manual_seed(7)
+    for N, C in ((7001, 64), (300, 1024), (129, 192)):
+        x = (torch.randn(N, C) * 0.3 + 25.0).bfloat16()
+        res = torch.randn(N, C).bfloat16()
+        bn = torch.nn.BatchNorm1d(C).to(_dev())
+        ref_bn = torch.nn.BatchNorm1d(C)
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+            ref_bn.weight.copy_(bn.weight.cpu()); ref_bn.bias.copy_(bn.bias.cpu())
+        xr, rr = x.float().requires_grad_(True), res.float().requires_grad_(True)
+        zr = torch.nn.functional.elu(ref_bn(xr) + rr)
+        g = torch.randn(N, C).bfloat16()
+        zr.backward(g.float())
+        xd, rd = x.to(_dev()).requires_grad_(True), res.to(_dev()).requires_grad_(True)
+        z = SP.batch_norm_rows(xd, bn, True, SP.ACT_ELU, rd)
+        z.backward(g.to(_dev()))
+        _close(z, zr, 2e-2, 'fused bn fwd')
+        _close(xd.grad, xr.grad, 3e-2, 'fused bn dx')
+        _close(rd.grad, rr.grad, 2e-2, 'fused bn dres')
+        _close(bn.weight.grad, ref_bn.weight.grad, 2e-2, 'fused bn dgamma')
+        _close(bn.running_mean, ref_bn.running_mean, 1e-3, 'running mean')
+        _close(bn.running_var, ref_bn.running_var, 2e-2, 'running var')
