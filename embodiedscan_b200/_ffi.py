@@ -55,6 +55,8 @@ SIGNATURES = {
     'esb_conv2d_direct_dgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_direct_wgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),
     'esb_maxpool2d_nhwc': ('pp' + 'iiiiiiii' + 'p', 'i'),
+    'esb_attn_fwd': ('pppppp' + 'iiii' + 'f' + 'p', 'i'),
+    'esb_attn_bwd': ('ppppppppppp' + 'iiii' + 'f' + 'p', 'i'),
     'esb_paint_meta_bytes': ('', 'i'),
     'esb_paint_fwd': ('pppqfppipiiiffppip', 'i'),
     'esb_paint_bwd': ('pppqfppipiiiffpip', 'i'),

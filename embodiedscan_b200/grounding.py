@@ -21,6 +21,8 @@ import zlib
 from typing import Dict, List, Optional
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -114,6 +116,45 @@ class PositionEmbeddingLearned(nn.Module):
         return self.position_embedding_head(xyz.transpose(1, 2).contiguous()).transpose(1, 2).contiguous()
 
 
+class _FlashAttention(torch.autograd.Function):
+    """softmax(q k^T * scale + key padding) v for 32-channel heads on the library's tcgen05 flash-attention tiles
+    (csrc/attn_tc.cu), forward and backward. q (B,H,Lq,32), k / v (B,H,Lk,32) bf16 contiguous; key_pad (B,Lk) bool or None."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_pad, scale):
+        from . import _ffi
+        B, H, Lq, D = q.shape
+        Lk = k.shape[2]
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        pad = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+        o = torch.empty_like(q)
+        lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+        _ffi.call('esb_attn_fwd', q.data_ptr(), k.data_ptr(), v.data_ptr(), _ffi.ptr(pad), o.data_ptr(), lse.data_ptr(), B, H, Lq,
+                  Lk, float(scale), _ffi.stream())
+        ctx.save_for_backward(q, k, v, o, lse, pad)
+        ctx.scale = float(scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        from . import _ffi
+        q, k, v, o, lse, pad = ctx.saved_tensors
+        B, H, Lq, D = q.shape
+        Lk = k.shape[2]
+        do = do.contiguous()
+        dq = torch.zeros((B, H, Lq, D), dtype=torch.float32, device=q.device)
+        dk, dv = torch.empty_like(k), torch.empty_like(v)
+        delta = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+        _ffi.call('esb_attn_bwd', q.data_ptr(), k.data_ptr(), v.data_ptr(), _ffi.ptr(pad), o.data_ptr(), do.data_ptr(),
+                  lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, Lq, Lk, ctx.scale,
+                  _ffi.stream())
+        return dq.to(q.dtype), dk, dv, None, None
+
+
+def flash_attention(q, k, v, key_pad=None, scale=None):
+    return _FlashAttention.apply(q, k, v, key_pad, scale if scale is not None else q.shape[-1] ** -0.5)
+
+
 class MultiheadAttention(nn.Module):
     """mmcv.cnn.bricks.transformer.MultiheadAttention (†upstream) with batch_first=True, no dropout: positional
     encodings are added to query / key (never to value), the result is added to ``identity`` (= the un-encoded query)."""
@@ -135,6 +176,18 @@ class MultiheadAttention(nn.Module):
             query = query + query_pos
         if key_pos is not None:
             key = key + key_pos
+        E, H = self.embed_dims, self.num_heads
+        if (query.is_cuda and attn_mask is None and E // H == 32 and torch.is_autocast_enabled()
+                and torch.get_autocast_gpu_dtype() == torch.bfloat16 and os.environ.get('ESB200_ATTN', 'own') == 'own'):
+            # the projections are plain library GEMMs; the attention core runs on the library's tcgen05 flash tiles
+            W, bias = self.attn.in_proj_weight, self.attn.in_proj_bias
+            B, Lq, Lk = query.shape[0], query.shape[1], key.shape[1]
+            q = F.linear(query, W[:E], bias[:E]).view(B, Lq, H, 32).transpose(1, 2)
+            k = F.linear(key, W[E:2 * E], bias[E:2 * E]).view(B, Lk, H, 32).transpose(1, 2)
+            v = F.linear(value, W[2 * E:], bias[2 * E:]).view(B, Lk, H, 32).transpose(1, 2)
+            o = flash_attention(q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16), key_padding_mask)
+            out = F.linear(o.transpose(1, 2).reshape(B, Lq, E), self.attn.out_proj.weight, self.attn.out_proj.bias)
+            return identity + out
         out = self.attn(query, key, value, attn_mask=attn_mask, key_padding_mask=key_padding_mask, need_weights=False)[0]
         return identity + out
 

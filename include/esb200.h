@@ -161,6 +161,17 @@ int esb_conv2d_direct_wgrad(const void* x, const void* dy, float* dw_ohwi, int n
 int esb_maxpool2d_nhwc(const void* x, void* y, int n_img, int H, int W, int C, int k, int stride, int pad, int dtype,
                        void* stream);
 
+/* ---- attention core of the grounding decoder (self-, text- and 3D cross-attention of
+ * embodiedscan/models/layers/ground_transformer/decoder.py:89-95,151-177; †upstream nn.MultiheadAttention) as flash-attention
+ * tiles on tcgen05 / TMEM fed by TMA (csrc/attn_tc.cu). Head dimension 32. q (B,H,Lq,32), k / v (B,H,Lk,32), o bf16 contiguous;
+ * key_pad (B,Lk) uint8 (1 = ignore) or NULL; lse (B,H,Lq) fp32. Backward: delta (B,H,Lq) fp32 workspace, dq (B,H,Lq,32) fp32
+ * ZEROED BY THE CALLER (key tiles accumulate with vector atomics), dk / dv (B,H,Lk,32) bf16 written once. -------------------- */
+int esb_attn_fwd(const void* q, const void* k, const void* v, const unsigned char* key_pad, void* o, float* lse, int B, int H,
+                 int Lq, int Lk, float scale, void* stream);
+int esb_attn_bwd(const void* q, const void* k, const void* v, const unsigned char* key_pad, const void* o, const void* dout,
+                 const float* lse, float* delta, float* dq, void* dk, void* dv, int B, int H, int Lq, int Lk, float scale,
+                 void* stream);
+
 /* ---- point painting (batch_point_sample + apply_3d_transformation + batch_points_cam2img + F.grid_sample;
  * embodiedscan/models/layers/fusion_layers/point_fusion.py:208-311, structures/bbox_3d/utils.py:289-332) -------- */
 int esb_paint_meta_bytes(void);
