@@ -24,6 +24,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The step allocates hundreds of tensors whose sizes follow the data (row counts of the sparse maps differ per batch): with the
+# default segment allocator a fragmented pool answers with cudaFree + cudaMalloc cycles (100-400 ms stalls every few steps).
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -280,6 +283,7 @@ def main():
         opt = dict(lr=1e-4, weight_decay=1e-2, max_norm=35.0)
     else:
         from embodiedscan_b200.synth import add_grounding_prompt, mv_grounding_config
+        os.environ.setdefault('ESB200_TEXT_RANDOM_INIT', '1')     # synthetic benchmark: shapes, not RoBERTa's checkpoint
         cfg = mv_grounding_config('C4')
         opt = dict(lr=5e-4, weight_decay=5e-4, max_norm=10.0)
     model = MODELS.build(dict(cfg, compute_dtype=dtype)).to(dev).train()

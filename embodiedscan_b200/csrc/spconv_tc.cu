@@ -436,8 +436,10 @@ extern "C" int esb_spconv_tc_fwd(const void* x, const void* wt, const int* nbr, 
   long long row_tiles = (n_out + TC_M - 1) / TC_M;
   const int n_tile = (cout % 256 == 0 && row_tiles * (cout / 256) >= 148) ? 256
                      : (cout % 128 == 0 && row_tiles * (cout / 128) >= 148) ? 128 : 64;
-  // two row tiles per CTA (one filter stage, two accumulators) while the grid still covers the SMs twice over
-  const bool two = n_tile <= 128 && (row_tiles / 2) * (cout / n_tile) >= 2 * 148 && getenv("ESB200_SPCONV_MT1") == nullptr;
+  // Two row tiles per CTA (one filter stage, two accumulators, 256 producer threads) halve the filter traffic, but one
+  // 288-thread CTA per SM measured slower than two 160-thread CTAs (C2 step: 0.685 vs 0.700 of HBM peak, 46.8 vs 40.9 ms per
+  // step, profiles/r2_bench_ab.txt): opt-in through ESB200_SPCONV_MT2=1.
+  const bool two = n_tile <= 128 && (row_tiles / 2) * (cout / n_tile) >= 2 * 148 && getenv("ESB200_SPCONV_MT2") != nullptr;
   CUtensorMap tmw;
   {
     unsigned long long dims[2], str[1];

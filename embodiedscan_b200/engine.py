@@ -141,9 +141,10 @@ class FusedAdamW:
     """AdamW + global-norm clipping over the arena: two kernel launches per step, no host sync."""
 
     def __init__(self, arena: FlatArena, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_norm=10.0,
-                 world_size: int = 1):
+                 world_size: int = 1, lr_mult: Optional[torch.Tensor] = None):
         self.arena, self.lr, self.betas, self.eps, self.wd, self.max_norm = arena, lr, betas, eps, weight_decay, max_norm
         self.world = world_size
+        self.lr_mult = lr_mult                       # per-element learning-rate multiplier over the arena, or None
         dev = arena.flat.device
         self.m = torch.zeros_like(arena.flat)
         self.v = torch.zeros_like(arena.flat)
@@ -156,7 +157,7 @@ class FusedAdamW:
         ws = 1.0 / self.world                         # arena.grad holds the SUM over ranks
         call('esb_grad_clip_coef', ptr(a.grad), a.numel, float(self.max_norm if self.max_norm else 0.), ws,
              ptr(self.state), stream())
-        call('esb_adamw_step', ptr(a.flat), ptr(a.grad), ptr(self.m), ptr(self.v), None, a.numel, self.lr, self.betas[0],
+        call('esb_adamw_step', ptr(a.flat), ptr(a.grad), ptr(self.m), ptr(self.v), ptr(self.lr_mult), a.numel, self.lr, self.betas[0],
              self.betas[1], self.eps, self.wd, self.step_count, ws, ptr(self.state), stream())
 
     @property
@@ -168,7 +169,7 @@ class OptimWrapper:
     """``update_params(loss)`` of mmengine's OptimWrapper for the arena optimiser."""
 
     def __init__(self, model: nn.Module, lr=1e-3, weight_decay=1e-4, max_norm=10.0, process_group=None,
-                 bucket_bytes: int = 64 << 20, max_run_ahead: int = 0):
+                 bucket_bytes: int = 64 << 20, max_run_ahead: int = 0, paramwise_cfg: Optional[dict] = None):
         # max_run_ahead: how many optimiser steps the host may queue ahead of the device. 0 = wait for the step's last
         # kernel before returning (what reading the loss every iteration does). Unbounded run-ahead was measured to
         # produce sporadic 100-400 ms stalls one or two steps after an idle period (allocator / driver back-pressure)
@@ -178,8 +179,25 @@ class OptimWrapper:
         self.arena = FlatArena(model, bucket_bytes)
         world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.reducer = DataParallelReducer(self.arena, process_group)
-        self.optimizer = FusedAdamW(self.arena, lr=lr, weight_decay=weight_decay, max_norm=max_norm, world_size=world)
+        self.optimizer = FusedAdamW(self.arena, lr=lr, weight_decay=weight_decay, max_norm=max_norm, world_size=world,
+                                    lr_mult=self._lr_mult(model, paramwise_cfg))
         self.arena.zero_grad()
+
+    def _lr_mult(self, model, paramwise_cfg):
+        """mmengine `paramwise_cfg=dict(custom_keys={name_substring: dict(lr_mult=...)})` (the grounding config scales the
+        decoder by 0.1 and freezes the text encoder with 0.0: configs/grounding/mv-grounding_8xb12_embodiedscan-vg-9dof.py)
+        as ONE per-element multiplier over the arena, consumed by the fused AdamW kernel. The longest matching key wins."""
+        keys = (paramwise_cfg or {}).get('custom_keys') or {}
+        if not keys:
+            return None
+        names = {id(p): n for n, p in model.named_parameters()}
+        mult = torch.ones(self.arena.numel, dtype=torch.float32, device=self.arena.flat.device)
+        for p, o in zip(self.arena.params, self.arena.offsets):
+            name = names.get(id(p), '')
+            hit = [k for k in keys if k in name]
+            if hit:
+                mult[o:o + p.numel()] = float(keys[max(hit, key=len)].get('lr_mult', 1.0))
+        return mult
 
     def update_params(self, loss: torch.Tensor):
         loss.backward()

@@ -87,16 +87,21 @@ class SimpleTokenizer:
 
 
 def build_text_modules(t_type='roberta-base'):
-    """RoBERTa-base tokenizer + encoder (sparse_featfusion_grounder.py:107-110). Pretrained files are used when they are
-    resolvable offline; otherwise the same architecture is built from its config with random weights and the
-    stand-in tokenizer (synthetic-data benchmarking and parity tests need shapes, not the checkpoint)."""
+    """RoBERTa-base tokenizer + encoder (sparse_featfusion_grounder.py:107-110), loaded like the reference does
+    (`from_pretrained`, which downloads when the files are not cached). Only when ESB200_TEXT_RANDOM_INIT=1 is set — the
+    synthetic benchmarks and the parity tests, which need shapes and not the checkpoint — a failure to resolve the files
+    falls back to the same architecture with random weights and the stand-in tokenizer; otherwise the error propagates (a
+    grounder silently training on a random frozen text encoder is worse than one that refuses to start)."""
     from transformers import RobertaConfig, RobertaModel
     try:
         from transformers import RobertaTokenizerFast
-        tok = RobertaTokenizerFast.from_pretrained(t_type, local_files_only=True)
-        enc = RobertaModel.from_pretrained(t_type, local_files_only=True)
+        offline = os.environ.get('HF_HUB_OFFLINE') == '1' or os.environ.get('ESB200_TEXT_RANDOM_INIT') == '1'
+        tok = RobertaTokenizerFast.from_pretrained(t_type, local_files_only=offline)
+        enc = RobertaModel.from_pretrained(t_type, local_files_only=offline)
     except Exception:
-        warnings.warn(f"'{t_type}' is not available offline: random-init RobertaModel + SimpleTokenizer")
+        if os.environ.get('ESB200_TEXT_RANDOM_INIT') != '1':
+            raise
+        warnings.warn(f"'{t_type}' is not available: ESB200_TEXT_RANDOM_INIT=1 -> random-init RobertaModel + SimpleTokenizer")
         cfg = RobertaConfig(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1, pad_token_id=1,
                             bos_token_id=0, eos_token_id=2, layer_norm_eps=1e-5)
         tok, enc = SimpleTokenizer(cfg.vocab_size), RobertaModel(cfg)

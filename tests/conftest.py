@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# tests need the grounder's shapes, not RoBERTa's checkpoint (no network): opt in to the random-init text encoder
+os.environ.setdefault('ESB200_TEXT_RANDOM_INIT', '1')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

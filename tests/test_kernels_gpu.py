@@ -642,3 +642,12 @@ def test_fused_batchnorm_bf16_matches_reference():
         _close(bn.weight.grad, ref_bn.weight.grad, 2e-2, 'fused bn dgamma')
         _close(bn.running_mean, ref_bn.running_mean, 1e-3, 'running mean')
         _close(bn.running_var, ref_bn.running_var, 2e-2, 'running var')
+
+
+def test_flash_attention_tc_matches_softmax_attention():
+    """csrc/attn_tc.cu (tcgen05 flash attention, forward + dq / dk / dv) against fp32 softmax attention on bf16-rounded
+    operands: self-attention, padded keys, 3.5k keys, ragged sizes below one tile."""
+    rows = _run_child('attn_child.py')
+    bad = [r for r in rows if not r.get('ok', True)]
+    assert not bad, bad
+    assert sum(r['kind'] == 'attn' for r in rows) >= 6
