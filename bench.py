@@ -366,9 +366,14 @@ def main():
     import gc
     gc.collect()
     gc.freeze()        # setup objects (model, batches, profile records) leave the collector's working set
-    for j in range(3):             # pre-roll: after an idle period (barrier, gc, logging) the device runs slow for
-        step(j)                    # ~0.2 s and the backlog surfaces at the next host sync; drain it before timing
+    # pre-roll: after an idle period (barrier, gc, event bookkeeping of the roofline pass) single steps stall for 40-400 ms
+    # during roughly the next half second (seen at N = 1 and N = 2 alike, never later): run through it before timing
+    pre_t = [time.perf_counter()]
+    for j in range(max(3, min(args.steps, 20))):
+        step(j)
+        pre_t.append(time.perf_counter())
     torch.cuda.synchronize()
+    log('host ms per pre-roll step: ' + ' '.join(f'{1e3 * (b - a):.1f}' for a, b in zip(pre_t[:-1], pre_t[1:])))
     host_t = [time.perf_counter()]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

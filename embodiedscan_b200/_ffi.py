@@ -50,6 +50,9 @@ SIGNATURES = {
     'esb_conv2d_tma_fwd': ('ppppp' + 'iiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tma_wgrad': ('ppp' + 'iiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tma_dgrad': ('ppp' + 'iiiiiiiii' + 'p', 'i'),
+    'esb_conv3d_tma_fwd': ('ppppp' + 'iiiiiiiiii' + 'p', 'i'),
+    'esb_conv3d_tma_dgrad': ('ppp' + 'iiiiiiiii' + 'p', 'i'),
+    'esb_conv3d_tma_wgrad': ('ppp' + 'iiiiiiiii' + 'p', 'i'),
     'esb_stem7x7_tc': ('pppp' + 'iiii' + 'p', 'i'),
     'esb_conv2d_direct_fwd': ('ppppp' + 'iiiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_direct_dgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),

@@ -26,9 +26,9 @@ using namespace esb_tc;
 namespace {
 
 struct ConvGeom {
-  int tiles_w, tiles_h, tiles_n, n_blocks;   // tile grid; n_blocks = Cout / N_TILE
-  int TW, TH, TN;                            // output pixels per tile along w, h, image
-  int Wo, Ho, N;                             // output extent
+  int tiles_w, tiles_h, tiles_d, tiles_n, n_blocks;   // tile grid; n_blocks = Cout / N_TILE
+  int TW, TH, TD, TN;                        // output pixels per tile along w, h, d, image (2-D convolutions: d = 1)
+  int Wo, Ho, Do, N;                         // output extent
   int stride;                                // spacing of the A-box origin per output pixel (element strides of the tensor map)
   int cin, bc, nchunk, group;                // reduction channels per tap, channels per sub-tile, cin / bc, sub-tiles per stage
   int cout, relu;
@@ -36,7 +36,7 @@ struct ConvGeom {
   // filter taps as a table: input offset of the tap relative to (output pixel * stride) and its index in the stored filter.
   // forward: (kx - pad, ky - pad, tap); stride-1 dgrad: flipped taps; stride-2 dgrad: the taps of one output parity class.
   int ntaps;
-  short tap_dx[16], tap_dy[16], tap_w[16];
+  short tap_dx[27], tap_dy[27], tap_dz[27], tap_w[27];
 };
 
 constexpr int EPI_THREADS = 128;
@@ -71,10 +71,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
   const int n_sub = g.ntaps * g.nchunk;                        // sub-tiles (tap, channel chunk) per output tile
   const int n_it = (n_sub + g.group - 1) / g.group;            // pipeline stages per output tile
   const int bcb = g.bc * 2;                                    // bytes per sub-tile row
-  const int rows_box = g.TW * g.TH * g.TN;
+  const int rows_box = g.TW * g.TH * g.TD * g.TN;
   const uint32_t a_sub_bytes = (uint32_t)rows_box * bcb;       // what TMA delivers (<= 128 rows)
   const uint32_t b_sub_bytes = (uint32_t)N_TILE * bcb;
-  const int n_work = g.tiles_w * g.tiles_h * g.tiles_n * g.n_blocks;
+  const int n_work = g.tiles_w * g.tiles_h * g.tiles_d * g.tiles_n * g.n_blocks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -104,9 +104,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
         int t = work;
         const int tw = t % g.tiles_w; t /= g.tiles_w;
         const int th = t % g.tiles_h; t /= g.tiles_h;
+        const int td = t % g.tiles_d; t /= g.tiles_d;
         const int tn = t % g.tiles_n; t /= g.tiles_n;
         const int n0 = t * N_TILE;
-        const int x0 = tw * g.TW * g.stride, y0 = th * g.TH * g.stride, img0 = tn * g.TN;
+        const int x0 = tw * g.TW * g.stride, y0 = th * g.TH * g.stride, z0 = td * g.TD * g.stride, img0 = tn * g.TN;
         for (int i = 0; i < n_it; ++i, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
@@ -118,7 +119,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
           for (int j = 0; j < cnt; ++j) {
             const int q = q0 + j;
             const int tap = q / g.nchunk, ch = (q - tap * g.nchunk) * g.bc;
-            tma_load_4d(&tmx, &full_bar[s], a_base + j * (128 * bcb), ch, x0 + g.tap_dx[tap], y0 + g.tap_dy[tap], img0);
+            tma_load_5d(&tmx, &full_bar[s], a_base + j * (128 * bcb), ch, x0 + g.tap_dx[tap], y0 + g.tap_dy[tap],
+                        z0 + g.tap_dz[tap], img0);
             const int wtap = g.tap_w[tap];
             if (!B_MN) {           // rows = output channels, columns = (tap, input channel): K-major B
               tma_load_2d(&tmw, &full_bar[s], b_base + j * b_sub_bytes, wtap * g.cin + ch, n0);
@@ -181,14 +183,18 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
       int t = work;
       const int tw = t % g.tiles_w; t /= g.tiles_w;
       const int th = t % g.tiles_h; t /= g.tiles_h;
+      const int td = t % g.tiles_d; t /= g.tiles_d;
       const int tn = t % g.tiles_n; t /= g.tiles_n;
       const int n0 = t * N_TILE;
-      const int ow0 = tw * g.TW, oh0 = th * g.TH, img0 = tn * g.TN;
+      const int ow0 = tw * g.TW, oh0 = th * g.TH, od0 = td * g.TD, img0 = tn * g.TN;
       // this thread's output pixel
-      const int mi = m / (g.TH * g.TW), mr = m - mi * (g.TH * g.TW);
-      const int mh = mr / g.TW, mw = mr - mh * g.TW;
-      const bool valid = m < rows_box && img0 + mi < g.N && oh0 + mh < g.Ho && ow0 + mw < g.Wo;
-      const long long pix = ((long long)(img0 + mi) * g.Ho + (oh0 + mh)) * g.Wo + (ow0 + mw);
+      int mr = m;
+      const int mw = mr % g.TW; mr /= g.TW;
+      const int mh = mr % g.TH; mr /= g.TH;
+      const int md = mr % g.TD;
+      const int mi = mr / g.TD;
+      const bool valid = m < rows_box && img0 + mi < g.N && od0 + md < g.Do && oh0 + mh < g.Ho && ow0 + mw < g.Wo;
+      const long long pix = (((long long)(img0 + mi) * g.Do + (od0 + md)) * g.Ho + (oh0 + mh)) * g.Wo + (ow0 + mw);
       const uint32_t as = tcount & 1;
       mbar_wait(&tfull_bar[as], (tcount >> 1) & 1);
       tc_fence_after();
@@ -249,7 +255,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
         fence_proxy_async();                                   // generic-proxy writes -> visible to the TMA store
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
-          tma_store_4d(&tmy, smem_u32(crow), n0 + c0, ow0, oh0, img0);
+          tma_store_5d(&tmy, smem_u32(crow), n0 + c0, ow0, oh0, od0, img0);
           tma_store_commit();
         }
       }
@@ -263,19 +269,19 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
   }
 }
 
-// pick the output-tile extent (TW x TH x TN <= 128 pixels) that wastes the fewest MMA rows over the whole output
-void choose_tile(int Wo, int Ho, int N, int* TW, int* TH, int* TN) {
+// pick the output-tile extent (TW x TH x TD x TN <= 128 pixels) that wastes the fewest MMA rows over the whole output
+void choose_tile(int Wo, int Ho, int Do, int N, int* TW, int* TH, int* TD, int* TN) {
   double best = -1.0;
-  *TW = *TH = *TN = 1;
-  for (int tw = 1; tw <= Wo && tw <= 128; ++tw) {
-    for (int th = 1; th <= Ho && tw * th <= 128; ++th) {
-      int tn = 1;
-      if (tw == Wo && th == Ho) tn = 128 / (tw * th) < N ? 128 / (tw * th) : N;
-      const long long tiles = (long long)esb_div_up(Wo, tw) * esb_div_up(Ho, th) * esb_div_up(N, tn);
-      const double eff = (double)Wo * Ho * N / ((double)tiles * 128.0) + 1e-6 * tw;   // ties: longer contiguous rows
-      if (eff > best) { best = eff; *TW = tw; *TH = th; *TN = tn; }
-    }
-  }
+  *TW = *TH = *TD = *TN = 1;
+  for (int tw = 1; tw <= Wo && tw <= 128; ++tw)
+    for (int th = 1; th <= Ho && tw * th <= 128; ++th)
+      for (int td = 1; td <= Do && tw * th * td <= 128; ++td) {
+        int tn = 1;
+        if (tw == Wo && th == Ho && td == Do) tn = 128 / (tw * th * td) < N ? 128 / (tw * th * td) : N;
+        const long long tiles = (long long)esb_div_up(Wo, tw) * esb_div_up(Ho, th) * esb_div_up(Do, td) * esb_div_up(N, tn);
+        const double eff = (double)Wo * Ho * Do * N / ((double)tiles * 128.0) + 1e-6 * tw;   // ties: longer contiguous rows
+        if (eff > best) { best = eff; *TW = tw; *TH = th; *TD = td; *TN = tn; }
+      }
 }
 
 template <int N_TILE, bool B_MN>
@@ -298,7 +304,7 @@ int launch(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tm
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long n_work = (long long)g.tiles_w * g.tiles_h * g.tiles_n * g.n_blocks;
+  const long long n_work = (long long)g.tiles_w * g.tiles_h * g.tiles_d * g.tiles_n * g.n_blocks;
   const int per_sm = (smem <= 110 * 1024 && 2 * N_TILE * 2 <= 512) ? 2 : 1;
   long long grid = (long long)sms * per_sm;
   if (grid > n_work) grid = n_work;
@@ -306,31 +312,38 @@ int launch(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tm
   return ESB_OK;
 }
 
-// One launch: `in` (N, Hi, Wi, Ci) -> `out` viewed as (N, Ho, Wo, Co) with the given byte strides (a parity class of dx is a
-// strided view), taps from the table in `g`. taps_total = kh*kw of the stored filter (extent of its tensor map).
-int conv_tma_run(const void* in, const void* w, const float* bias, const void* res, void* out, int N, int Hi, int Wi, int Ci,
-                 int Ho, int Wo, int Co, int taps_total, int stride, int relu, bool dgrad, ConvGeom g,
-                 unsigned long long out_sw, unsigned long long out_sh, unsigned long long out_sn, cudaStream_t stream) {
-  g.Wo = Wo; g.Ho = Ho; g.N = N;
+// One launch: `in` (N, Di, Hi, Wi, Ci) -> `out` viewed as (N, Do, Ho, Wo, Co) with the given byte strides (a parity class of dx
+// is a strided view), taps from the table in `g`. taps_total = taps of the stored filter (extent of its tensor map).
+// 2-D convolutions are the Di = Do = 1 case of the same rank-5 tensor maps.
+int conv_tma_run(const void* in, const void* w, const float* bias, const void* res, void* out, int N, int Di, int Hi, int Wi,
+                 int Ci, int Do, int Ho, int Wo, int Co, int taps_total, int stride, int relu, bool dgrad, ConvGeom g,
+                 unsigned long long out_sw, unsigned long long out_sh, unsigned long long out_sd, unsigned long long out_sn,
+                 cudaStream_t stream) {
+  g.Wo = Wo; g.Ho = Ho; g.Do = Do; g.N = N;
   g.stride = stride;
   g.cin = Ci; g.cout = Co; g.relu = relu;
   g.bc = Ci >= 64 ? 64 : Ci;
   g.nchunk = Ci / g.bc;
   g.group = 64 / g.bc;
-  choose_tile(Wo, Ho, N, &g.TW, &g.TH, &g.TN);
-  g.tiles_w = esb_div_up(Wo, g.TW); g.tiles_h = esb_div_up(Ho, g.TH); g.tiles_n = esb_div_up(N, g.TN);
+  choose_tile(Wo, Ho, Do, N, &g.TW, &g.TH, &g.TD, &g.TN);
+  g.tiles_w = esb_div_up(Wo, g.TW); g.tiles_h = esb_div_up(Ho, g.TH); g.tiles_d = esb_div_up(Do, g.TD);
+  g.tiles_n = esb_div_up(N, g.TN);
   const int n_tile = Co >= 256 ? 256 : Co;
   g.n_blocks = Co / n_tile;
+  const int sd = Di > 1 ? stride : 1;          // a depth-1 (2-D) problem has nothing to stride over
   CUtensorMap tmx, tmw, tmy;
-  {   // activations: {C, W, H, N}, box {bc, span_w, span_h, TN}, element strides {1, s, s, 1}
-    unsigned long long dims[4] = {(unsigned long long)Ci, (unsigned long long)Wi, (unsigned long long)Hi, (unsigned long long)N};
-    unsigned long long str[3] = {(unsigned long long)Ci * 2, (unsigned long long)Wi * Ci * 2, (unsigned long long)Hi * Wi * Ci * 2};
-    unsigned box[4] = {(unsigned)g.bc, (unsigned)((g.TW - 1) * stride + 1), (unsigned)((g.TH - 1) * stride + 1), (unsigned)g.TN};
-    unsigned es[4] = {1, (unsigned)stride, (unsigned)stride, 1};
-    int rc = esb_tma_encode(&tmx, in, 4, dims, str, box, es, g.bc * 2 >= 128 ? 128 : g.bc * 2);
+  {   // activations: {C, W, H, D, N}, box {bc, span_w, span_h, span_d, TN}, element strides {1, s, s, s, 1}
+    unsigned long long dims[5] = {(unsigned long long)Ci, (unsigned long long)Wi, (unsigned long long)Hi, (unsigned long long)Di,
+                                  (unsigned long long)N};
+    unsigned long long str[4] = {(unsigned long long)Ci * 2, (unsigned long long)Wi * Ci * 2, (unsigned long long)Hi * Wi * Ci * 2,
+                                 (unsigned long long)Di * Hi * Wi * Ci * 2};
+    unsigned box[5] = {(unsigned)g.bc, (unsigned)((g.TW - 1) * stride + 1), (unsigned)((g.TH - 1) * stride + 1),
+                       (unsigned)((g.TD - 1) * sd + 1), (unsigned)g.TN};
+    unsigned es[5] = {1, (unsigned)stride, (unsigned)stride, (unsigned)sd, 1};
+    int rc = esb_tma_encode(&tmx, in, 5, dims, str, box, es, g.bc * 2 >= 128 ? 128 : g.bc * 2);
     if (rc != ESB_OK) return rc;
   }
-  if (!dgrad) {   // OHWI (Co, taps*Ci): box {bc, n_tile}
+  if (!dgrad) {   // O..I (Co, taps*Ci): box {bc, n_tile}
     unsigned long long dims[2] = {(unsigned long long)taps_total * Ci, (unsigned long long)Co};
     unsigned long long str[1] = {(unsigned long long)taps_total * Ci * 2};
     unsigned box[2] = {(unsigned)g.bc, (unsigned)n_tile};
@@ -344,12 +357,13 @@ int conv_tma_run(const void* in, const void* w, const float* bias, const void* r
     int rc = esb_tma_encode(&tmw, w, 2, dims, str, box, nullptr, na * 2);
     if (rc != ESB_OK) return rc;
   }
-  {   // output store: {Co, Wo, Ho, N} with the caller's strides, box {<=64 channels, TW, TH, TN}
+  {   // output store: {Co, Wo, Ho, Do, N} with the caller's strides, box {<=64 channels, TW, TH, TD, TN}
     const int cb = n_tile < 64 ? n_tile : 64;
-    unsigned long long dims[4] = {(unsigned long long)Co, (unsigned long long)Wo, (unsigned long long)Ho, (unsigned long long)N};
-    unsigned long long str[3] = {out_sw, out_sh, out_sn};
-    unsigned box[4] = {(unsigned)cb, (unsigned)g.TW, (unsigned)g.TH, (unsigned)g.TN};
-    int rc = esb_tma_encode(&tmy, out, 4, dims, str, box, nullptr, cb * 2);
+    unsigned long long dims[5] = {(unsigned long long)Co, (unsigned long long)Wo, (unsigned long long)Ho, (unsigned long long)Do,
+                                  (unsigned long long)N};
+    unsigned long long str[4] = {out_sw, out_sh, out_sd, out_sn};
+    unsigned box[5] = {(unsigned)cb, (unsigned)g.TW, (unsigned)g.TH, (unsigned)g.TD, (unsigned)g.TN};
+    int rc = esb_tma_encode(&tmy, out, 5, dims, str, box, nullptr, cb * 2);
     if (rc != ESB_OK) return rc;
   }
   int rc;
@@ -373,28 +387,103 @@ bool channels_ok(int c) { return c == 16 || c == 32 || (c >= 64 && c % 64 == 0);
 
 }  // namespace
 
+namespace {
+
+// forward of a (kd, kh, kw) convolution on (n, D, H, W, cin); kd = D = 1 for the 2-D entry point
+int conv_fwd_any(const char* who, const void* x, const void* w, const float* bias, const void* residual, void* y, int n, int D,
+                 int H, int W, int cin, int cout, int kd, int kh, int kw, int stride, int pad, int relu, cudaStream_t stream) {
+  const int pd = kd > 1 ? pad : 0;
+  if (!(channels_ok(cin) && channels_ok(cout))) { esb_set_error("%s: channels must be 16, 32 or a multiple of 64", who); return ESB_EINVAL; }
+  if (!(cout <= 256 ? (cout & (cout - 1)) == 0 : cout % 256 == 0)) {
+    esb_set_error("%s: Cout must be a power of two <= 256 or a multiple of 256", who);
+    return ESB_EINVAL;
+  }
+  if (!(kd >= 1 && kh >= 1 && kw >= 1 && kd * kh * kw <= 27 && stride >= 1 && stride <= 8 && pad >= 0)) {
+    esb_set_error("%s: bad filter geometry (at most 27 taps)", who);
+    return ESB_EINVAL;
+  }
+  const int Do = (D + 2 * pd - kd) / (D > 1 ? stride : 1) + 1, Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  if (Do <= 0 || Ho <= 0 || Wo <= 0) { esb_set_error("%s: empty output", who); return ESB_EINVAL; }
+  if (n == 0) return ESB_OK;
+  ConvGeom g{};
+  for (int kz = 0; kz < kd; ++kz)
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx) {
+        g.tap_dx[g.ntaps] = (short)(kx - pad);
+        g.tap_dy[g.ntaps] = (short)(ky - pad);
+        g.tap_dz[g.ntaps] = (short)(kz - pd);
+        g.tap_w[g.ntaps] = (short)g.ntaps;
+        ++g.ntaps;
+      }
+  const unsigned long long px = (unsigned long long)cout * 2;
+  return conv_tma_run(x, w, bias, residual, y, n, D, H, W, cin, Do, Ho, Wo, cout, kd * kh * kw, stride, relu, false, g, px,
+                      (unsigned long long)Wo * px, (unsigned long long)Ho * Wo * px, (unsigned long long)Do * Ho * Wo * px, stream);
+}
+
+// input gradient, stride 1 or 2: one launch per parity class of dx (see esb_conv2d_tma_dgrad)
+int conv_dgrad_any(const char* who, const void* dy, const void* w, void* dx, int n, int D, int H, int W, int cin, int cout, int kd,
+                   int kh, int kw, int stride, int pad, cudaStream_t stream) {
+  const int pd = kd > 1 ? pad : 0, sd = D > 1 ? stride : 1;
+  if (!(channels_ok(cin) && channels_ok(cout))) { esb_set_error("%s: channels must be 16, 32 or a multiple of 64", who); return ESB_EINVAL; }
+  if (!(cin <= 256 ? (cin & (cin - 1)) == 0 : cin % 256 == 0)) {
+    esb_set_error("%s: Cin must be a power of two <= 256 or a multiple of 256", who);
+    return ESB_EINVAL;
+  }
+  if (!(kd >= 1 && kh >= 1 && kw >= 1 && kd * kh * kw <= 27 && pad >= 0 && pad < kh && pad < kw && (stride == 1 || stride == 2))) {
+    esb_set_error("%s: bad filter geometry", who);
+    return ESB_EINVAL;
+  }
+  const int Do = (D + 2 * pd - kd) / sd + 1, Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  if (Do <= 0 || Ho <= 0 || Wo <= 0) { esb_set_error("%s: empty output", who); return ESB_EINVAL; }
+  if (n == 0) return ESB_OK;
+  const unsigned long long px = (unsigned long long)cin * 2, row = (unsigned long long)W * px, slab = (unsigned long long)H * row,
+                           img = (unsigned long long)D * slab;
+  if (stride == 2 && (kh < 2 || kw < 2 || (D > 1 && kd < 2)))   // a 1-wide filter leaves whole parity classes of dx untouched
+    ESB_CUDA_CALL(cudaMemsetAsync(dx, 0, (size_t)n * img, stream));
+  for (int pz = 0; pz < sd; ++pz)
+    for (int ph = 0; ph < stride; ++ph)
+      for (int pw = 0; pw < stride; ++pw) {
+        const int Dc = (D - pz + sd - 1) / sd, Hc = (H - ph + stride - 1) / stride, Wc = (W - pw + stride - 1) / stride;
+        if (Dc <= 0 || Hc <= 0 || Wc <= 0) continue;
+        ConvGeom g{};
+        for (int kz = 0; kz < kd; ++kz)
+          for (int ky = 0; ky < kh; ++ky)
+            for (int kx = 0; kx < kw; ++kx) {
+              // dy pixel = (stride * i + n) / stride for class pixel i; only taps of matching parity contribute
+              const int nz = pz + pd - kz, ny = ph + pad - ky, nx = pw + pad - kx;
+              if (((nz % sd) + sd) % sd != 0 || ((ny % stride) + stride) % stride != 0 || ((nx % stride) + stride) % stride != 0) continue;
+              g.tap_dx[g.ntaps] = (short)(nx >= 0 ? nx / stride : -((-nx) / stride));
+              g.tap_dy[g.ntaps] = (short)(ny >= 0 ? ny / stride : -((-ny) / stride));
+              g.tap_dz[g.ntaps] = (short)(nz >= 0 ? nz / sd : -((-nz) / sd));
+              g.tap_w[g.ntaps] = (short)((kz * kh + ky) * kw + kx);
+              ++g.ntaps;
+            }
+        if (g.ntaps == 0) continue;                             // no tap reaches this class: zeroed by the memset above
+        uint8_t* base = (uint8_t*)dx + (unsigned long long)pz * slab + (unsigned long long)ph * row + (unsigned long long)pw * px;
+        int rc = conv_tma_run(dy, w, nullptr, nullptr, base, n, Do, Ho, Wo, cout, Dc, Hc, Wc, cin, kd * kh * kw, 1, 0, true, g,
+                              (unsigned long long)stride * px, (unsigned long long)stride * row, (unsigned long long)sd * slab, img,
+                              stream);
+        if (rc != ESB_OK) return rc;
+      }
+  return ESB_OK;
+}
+
+}  // namespace
+
 // y (n,Ho,Wo,cout) = act(conv(x (n,H,W,cin), w_ohwi (cout,kh,kw,cin)) + bias + residual), NHWC bf16, fp32 accumulate.
 // bias fp32 (cout) or NULL; residual bf16 (n,Ho,Wo,cout) or NULL. cin, cout in {16, 32, 64k}; cout <= 256 or a multiple of 256.
 extern "C" int esb_conv2d_tma_fwd(const void* x, const void* w_ohwi, const float* bias, const void* residual, void* y,
                                   int n_img, int H, int W, int cin, int cout, int kh, int kw, int stride, int pad, int relu,
                                   void* stream_) {
-  ESB_CHECK_ARG(channels_ok(cin) && channels_ok(cout), "esb_conv2d_tma_fwd: channels must be 16, 32 or a multiple of 64");
-  ESB_CHECK_ARG(cout <= 256 || cout % 256 == 0, "esb_conv2d_tma_fwd: Cout above 256 must be a multiple of 256");
-  ESB_CHECK_ARG(cout <= 256 ? (cout & (cout - 1)) == 0 : true, "esb_conv2d_tma_fwd: Cout <= 256 must be a power of two");
-  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && stride >= 1 && stride <= 8 && pad >= 0, "esb_conv2d_tma_fwd: bad filter geometry");
-  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
-  ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tma_fwd: empty output");
-  if (n_img == 0) return ESB_OK;
-  ESB_CHECK_ARG(kh * kw <= 16, "esb_conv2d_tma_fwd: at most 16 filter taps");
-  ConvGeom g{};
-  g.ntaps = kh * kw;
-  for (int t = 0; t < g.ntaps; ++t) {
-    g.tap_dx[t] = (short)(t % kw - pad);
-    g.tap_dy[t] = (short)(t / kw - pad);
-    g.tap_w[t] = (short)t;
-  }
-  return conv_tma_run(x, w_ohwi, bias, residual, y, n_img, H, W, cin, Ho, Wo, cout, kh * kw, stride, relu, false, g,
-                      (unsigned long long)cout * 2, (unsigned long long)Wo * cout * 2, (unsigned long long)Ho * Wo * cout * 2,
+  return conv_fwd_any("esb_conv2d_tma_fwd", x, w_ohwi, bias, residual, y, n_img, 1, H, W, cin, cout, 1, kh, kw, stride, pad, relu,
+                      (cudaStream_t)stream_);
+}
+
+// The same kernel on (n, D, H, W, cin) volumes (rank-5 tensor maps): the dense Conv3d stack of the occupancy neck
+// (embodiedscan/models/necks/imvoxel_neck.py:86-129). w_odhwi (cout, k, k, k, cin), NDHWC bf16.
+extern "C" int esb_conv3d_tma_fwd(const void* x, const void* w_odhwi, const float* bias, const void* residual, void* y, int n,
+                                  int D, int H, int W, int cin, int cout, int k, int stride, int pad, int relu, void* stream_) {
+  return conv_fwd_any("esb_conv3d_tma_fwd", x, w_odhwi, bias, residual, y, n, D, H, W, cin, cout, k, k, k, stride, pad, relu,
                       (cudaStream_t)stream_);
 }
 
@@ -405,38 +494,14 @@ extern "C" int esb_conv2d_tma_fwd(const void* x, const void* w_ohwi, const float
 // except for classes no tap reaches (1x1 / stride 2).
 extern "C" int esb_conv2d_tma_dgrad(const void* dy, const void* w_ohwi, void* dx, int n_img, int H, int W, int cin, int cout,
                                     int kh, int kw, int stride, int pad, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  ESB_CHECK_ARG(channels_ok(cin) && channels_ok(cout), "esb_conv2d_tma_dgrad: channels must be 16, 32 or a multiple of 64");
-  ESB_CHECK_ARG(cin <= 256 ? (cin & (cin - 1)) == 0 : cin % 256 == 0, "esb_conv2d_tma_dgrad: Cin must be a power of two <= 256 or a multiple of 256");
-  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && kh * kw <= 16 && pad >= 0 && pad < kh && pad < kw && (stride == 1 || stride == 2),
-                "esb_conv2d_tma_dgrad: bad filter geometry");
-  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
-  ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tma_dgrad: empty output");
-  if (n_img == 0) return ESB_OK;
-  const unsigned long long px = (unsigned long long)cin * 2, row = (unsigned long long)W * px, img = (unsigned long long)H * row;
-  if (stride == 2 && (kh < 2 || kw < 2))     // a 1-wide filter leaves whole parity classes of dx untouched: they are zero
-    ESB_CUDA_CALL(cudaMemsetAsync(dx, 0, (size_t)n_img * img, stream));
-  for (int ph = 0; ph < stride; ++ph)
-    for (int pw = 0; pw < stride; ++pw) {
-      const int Hc = (H - ph + stride - 1) / stride, Wc = (W - pw + stride - 1) / stride;    // pixels of this parity class
-      if (Hc <= 0 || Wc <= 0) continue;
-      ConvGeom g{};
-      for (int ky = 0; ky < kh; ++ky)
-        for (int kx = 0; kx < kw; ++kx) {
-          const int ny = ph + pad - ky, nx = pw + pad - kx;      // dy pixel = (stride * i + n) / stride for class pixel i
-          if (((ny % stride) + stride) % stride != 0 || ((nx % stride) + stride) % stride != 0) continue;
-          g.tap_dx[g.ntaps] = (short)(nx >= 0 ? nx / stride : -((-nx) / stride));
-          g.tap_dy[g.ntaps] = (short)(ny >= 0 ? ny / stride : -((-ny) / stride));
-          g.tap_w[g.ntaps] = (short)(ky * kw + kx);
-          ++g.ntaps;
-        }
-      uint8_t* base = (uint8_t*)dx + (unsigned long long)ph * row + (unsigned long long)pw * px;
-      if (g.ntaps == 0) continue;                               // no tap reaches this class: zeroed by the memset above
-      int rc = conv_tma_run(dy, w_ohwi, nullptr, nullptr, base, n_img, Ho, Wo, cout, Hc, Wc, cin, kh * kw, 1, 0, true, g,
-                            (unsigned long long)stride * px, (unsigned long long)stride * row, img, stream);
-      if (rc != ESB_OK) return rc;
-    }
-  return ESB_OK;
+  return conv_dgrad_any("esb_conv2d_tma_dgrad", dy, w_ohwi, dx, n_img, 1, H, W, cin, cout, 1, kh, kw, stride, pad,
+                        (cudaStream_t)stream_);
+}
+
+extern "C" int esb_conv3d_tma_dgrad(const void* dy, const void* w_odhwi, void* dx, int n, int D, int H, int W, int cin, int cout,
+                                    int k, int stride, int pad, void* stream_) {
+  return conv_dgrad_any("esb_conv3d_tma_dgrad", dy, w_odhwi, dx, n, D, H, W, cin, cout, k, k, k, stride, pad,
+                        (cudaStream_t)stream_);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -603,9 +668,9 @@ extern "C" int esb_stem7x7_tc(const void* x, const void* w_ohwi, const float* bi
 namespace {
 
 struct WgradGeom {
-  int tiles_w, tiles_h, tiles_n;     // pixel-tile grid over the OUTPUT pixels
-  int TW, TH, TN;                    // TW*TH*TN == 64
-  int kh, kw, stride, pad;
+  int tiles_w, tiles_h, tiles_d, tiles_n;     // pixel-tile grid over the OUTPUT pixels
+  int TW, TH, TD, TN;                // TW*TH*TD*TN == 64
+  int kd, kh, kw, stride, sd, pad, pd;   // sd / pd: stride / padding along depth (1 / 0 for 2-D convolutions)
   int cin, cout, aw, atoms_per_slice, chunks_per_tap;   // aw = channels per atom = min(cin, 64)
   int stages, tiles_per_cta;
 };
@@ -628,8 +693,8 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_cons
   uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int taps = g.kh * g.kw;
-  const int n_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  const int taps = g.kd * g.kh * g.kw;
+  const int n_tiles = g.tiles_w * g.tiles_h * g.tiles_d * g.tiles_n;
   const int t_beg = blockIdx.x * g.tiles_per_cta;
   const int t_end = min(n_tiles, t_beg + g.tiles_per_cta);
   if (t_beg >= n_tiles) return;                                // uniform for the whole CTA
@@ -663,7 +728,8 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_cons
         int t = t_beg + it;
         const int tw = t % g.tiles_w; t /= g.tiles_w;
         const int th = t % g.tiles_h; t /= g.tiles_h;
-        const int ox0 = tw * g.TW, oy0 = th * g.TH, img0 = t * g.TN;
+        const int td = t % g.tiles_d; t /= g.tiles_d;
+        const int ox0 = tw * g.TW, oy0 = th * g.TH, oz0 = td * g.TD, img0 = t * g.TN;
         const int s = it % STAGES;
         mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
         mbar_expect_tx(&full_bar[s], (uint32_t)n_valid * a_atom_bytes + B_BYTES);
@@ -672,13 +738,14 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_cons
         for (int a = 0; a < n_valid; ++a) {
           const int ga = atom0 + a;
           const int tap = ga / g.chunks_per_tap, ch0 = (ga - tap * g.chunks_per_tap) * g.aw;
-          const int ky = tap / g.kw, kx = tap - ky * g.kw;
-          tma_load_4d(&tmx, &full_bar[s], a_base + a * a_atom_bytes, ch0, ox0 * g.stride - g.pad + kx, oy0 * g.stride - g.pad + ky,
-                      img0);
+          const int kz = tap / (g.kh * g.kw), kr = tap - kz * (g.kh * g.kw);
+          const int ky = kr / g.kw, kx = kr - ky * g.kw;
+          tma_load_5d(&tmx, &full_bar[s], a_base + a * a_atom_bytes, ch0, ox0 * g.stride - g.pad + kx, oy0 * g.stride - g.pad + ky,
+                      oz0 * g.sd - g.pd + kz, img0);
         }
 #pragma unroll
         for (int b = 0; b < N_TILE / NA; ++b)
-          tma_load_4d(&tmdy, &full_bar[s], b_base + b * (64 * NA * 2), co0 + b * NA, ox0, oy0, img0);
+          tma_load_5d(&tmdy, &full_bar[s], b_base + b * (64 * NA * 2), co0 + b * NA, ox0, oy0, oz0, img0);
       }
     }
   } else if (warp == 1) {
@@ -754,7 +821,7 @@ int launch_wgrad_tma(const CUtensorMap& tmx, const CUtensorMap& tmdy, float* dw,
   auto kern = conv_tma_wgrad_kernel<N_TILE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { esb_set_error("conv_tma_wgrad: smem attr: %s", cudaGetErrorString(e)); return ESB_ECUDA; }
-  const long long n_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
+  const long long n_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_d * g.tiles_n;
   // ~2 CTAs per SM in total; every CTA walks a contiguous range of pixel tiles
   long long splits = (2LL * 148 + (long long)slices * n_blocks - 1) / ((long long)slices * n_blocks);
   if (splits > n_tiles) splits = n_tiles;
@@ -767,60 +834,85 @@ int launch_wgrad_tma(const CUtensorMap& tmx, const CUtensorMap& tmdy, float* dw,
 
 }  // namespace
 
-// dw_t (kh*kw*cin, cout) fp32, ZEROED BY THE CALLER: dW[co, ci, ky, kx] = dw_t[(ky*kw + kx)*cin + ci, co].
-// x (n,H,W,cin), dy (n,Ho,Wo,cout) bf16 NHWC; cin, cout in {16, 32, 64, 128, 256, 512, ...}.
-extern "C" int esb_conv2d_tma_wgrad(const void* x, const void* dy, float* dw_t, int n_img, int H, int W, int cin, int cout,
-                                    int kh, int kw, int stride, int pad, void* stream_) {
-  ESB_CHECK_ARG(channels_ok(cin) && channels_ok(cout), "esb_conv2d_tma_wgrad: channels must be 16, 32 or a multiple of 64");
-  ESB_CHECK_ARG(kh >= 1 && kw >= 1 && stride >= 1 && stride <= 8 && pad >= 0, "esb_conv2d_tma_wgrad: bad filter geometry");
-  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
-  ESB_CHECK_ARG(Ho > 0 && Wo > 0, "esb_conv2d_tma_wgrad: empty output");
+namespace {
+
+int conv_wgrad_any(const char* who, const void* x, const void* dy, float* dw_t, int n_img, int D, int H, int W, int cin, int cout,
+                   int kd, int kh, int kw, int stride, int pad, cudaStream_t stream) {
+  if (!(channels_ok(cin) && channels_ok(cout))) { esb_set_error("%s: channels must be 16, 32 or a multiple of 64", who); return ESB_EINVAL; }
+  if (!(kd >= 1 && kh >= 1 && kw >= 1 && stride >= 1 && stride <= 8 && pad >= 0)) { esb_set_error("%s: bad filter geometry", who); return ESB_EINVAL; }
+  const int pd = kd > 1 ? pad : 0, sd = D > 1 ? stride : 1;
+  const int Do = (D + 2 * pd - kd) / sd + 1, Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  if (Do <= 0 || Ho <= 0 || Wo <= 0) { esb_set_error("%s: empty output", who); return ESB_EINVAL; }
   if (n_img == 0) return ESB_OK;
   WgradGeom g{};
-  g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.cin = cin; g.cout = cout;
+  g.kd = kd; g.kh = kh; g.kw = kw; g.stride = stride; g.sd = sd; g.pad = pad; g.pd = pd; g.cin = cin; g.cout = cout;
   g.aw = cin < 64 ? cin : 64;
   g.atoms_per_slice = 128 / g.aw;
   g.chunks_per_tap = cin / g.aw;
   // pixel box of exactly 64 output pixels (powers of two): the one wasting the fewest zero-filled pixels
   double best = -1.0;
   for (int tw = 1; tw <= 64; tw *= 2)
-    for (int th = 1; tw * th <= 64; th *= 2) {
-      const int tn = 64 / (tw * th);
-      if ((tn > 1 && (tw < Wo || th < Ho)) || tn > 64) continue;      // several images per box only for whole (padded) images
-      const double tiles = (double)esb_div_up(Wo, tw) * esb_div_up(Ho, th) * esb_div_up(n_img, tn);
-      const double eff = (double)Wo * Ho * n_img / (tiles * 64.0) + 1e-6 * tw;
-      if (eff > best) { best = eff; g.TW = tw; g.TH = th; g.TN = tn; }
-    }
-  g.tiles_w = esb_div_up(Wo, g.TW); g.tiles_h = esb_div_up(Ho, g.TH); g.tiles_n = esb_div_up(n_img, g.TN);
+    for (int th = 1; tw * th <= 64; th *= 2)
+      for (int td = 1; tw * th * td <= 64; td *= 2) {
+        const int tn = 64 / (tw * th * td);
+        if (tn > 1 && (tw < Wo || th < Ho || td < Do)) continue;   // several images per box only for whole (padded) volumes
+        if (td > 1 && Do == 1) continue;
+        const double tiles = (double)esb_div_up(Wo, tw) * esb_div_up(Ho, th) * esb_div_up(Do, td) * esb_div_up(n_img, tn);
+        const double eff = (double)Wo * Ho * Do * n_img / (tiles * 64.0) + 1e-6 * tw;
+        if (eff > best) { best = eff; g.TW = tw; g.TH = th; g.TD = td; g.TN = tn; }
+      }
+  g.tiles_w = esb_div_up(Wo, g.TW); g.tiles_h = esb_div_up(Ho, g.TH); g.tiles_d = esb_div_up(Do, g.TD);
+  g.tiles_n = esb_div_up(n_img, g.TN);
   const int n_tile = cout >= 128 ? 128 : cout;
   const int n_blocks = cout / n_tile;
-  const int slices = esb_div_up(kh * kw * g.chunks_per_tap, g.atoms_per_slice);
+  const int slices = esb_div_up(kd * kh * kw * g.chunks_per_tap, g.atoms_per_slice);
   CUtensorMap tmx, tmdy;
   {
-    unsigned long long dims[4] = {(unsigned long long)cin, (unsigned long long)W, (unsigned long long)H, (unsigned long long)n_img};
-    unsigned long long str[3] = {(unsigned long long)cin * 2, (unsigned long long)W * cin * 2, (unsigned long long)H * W * cin * 2};
-    unsigned box[4] = {(unsigned)g.aw, (unsigned)((g.TW - 1) * stride + 1), (unsigned)((g.TH - 1) * stride + 1), (unsigned)g.TN};
-    unsigned es[4] = {1, (unsigned)stride, (unsigned)stride, 1};
-    int rc = esb_tma_encode(&tmx, x, 4, dims, str, box, es, g.aw * 2);
+    unsigned long long dims[5] = {(unsigned long long)cin, (unsigned long long)W, (unsigned long long)H, (unsigned long long)D,
+                                  (unsigned long long)n_img};
+    unsigned long long str[4] = {(unsigned long long)cin * 2, (unsigned long long)W * cin * 2, (unsigned long long)H * W * cin * 2,
+                                 (unsigned long long)D * H * W * cin * 2};
+    unsigned box[5] = {(unsigned)g.aw, (unsigned)((g.TW - 1) * stride + 1), (unsigned)((g.TH - 1) * stride + 1),
+                       (unsigned)((g.TD - 1) * sd + 1), (unsigned)g.TN};
+    unsigned es[5] = {1, (unsigned)stride, (unsigned)stride, (unsigned)sd, 1};
+    int rc = esb_tma_encode(&tmx, x, 5, dims, str, box, es, g.aw * 2);
     if (rc != ESB_OK) return rc;
   }
   {
     const int na = n_tile < 64 ? n_tile : 64;
-    unsigned long long dims[4] = {(unsigned long long)cout, (unsigned long long)Wo, (unsigned long long)Ho, (unsigned long long)n_img};
-    unsigned long long str[3] = {(unsigned long long)cout * 2, (unsigned long long)Wo * cout * 2, (unsigned long long)Ho * Wo * cout * 2};
-    unsigned box[4] = {(unsigned)na, (unsigned)g.TW, (unsigned)g.TH, (unsigned)g.TN};
-    int rc = esb_tma_encode(&tmdy, dy, 4, dims, str, box, nullptr, na * 2);
+    unsigned long long dims[5] = {(unsigned long long)cout, (unsigned long long)Wo, (unsigned long long)Ho, (unsigned long long)Do,
+                                  (unsigned long long)n_img};
+    unsigned long long str[4] = {(unsigned long long)cout * 2, (unsigned long long)Wo * cout * 2,
+                                 (unsigned long long)Ho * Wo * cout * 2, (unsigned long long)Do * Ho * Wo * cout * 2};
+    unsigned box[5] = {(unsigned)na, (unsigned)g.TW, (unsigned)g.TH, (unsigned)g.TD, (unsigned)g.TN};
+    int rc = esb_tma_encode(&tmdy, dy, 5, dims, str, box, nullptr, na * 2);
     if (rc != ESB_OK) return rc;
   }
   int rc;
   switch (n_tile) {
-    case 16: rc = launch_wgrad_tma<16>(tmx, tmdy, dw_t, g, slices, n_blocks, (cudaStream_t)stream_); break;
-    case 32: rc = launch_wgrad_tma<32>(tmx, tmdy, dw_t, g, slices, n_blocks, (cudaStream_t)stream_); break;
-    case 64: rc = launch_wgrad_tma<64>(tmx, tmdy, dw_t, g, slices, n_blocks, (cudaStream_t)stream_); break;
-    case 128: rc = launch_wgrad_tma<128>(tmx, tmdy, dw_t, g, slices, n_blocks, (cudaStream_t)stream_); break;
-    default: esb_set_error("esb_conv2d_tma_wgrad: unsupported Cout %d", cout); return ESB_EINVAL;
+    case 16: rc = launch_wgrad_tma<16>(tmx, tmdy, dw_t, g, slices, n_blocks, stream); break;
+    case 32: rc = launch_wgrad_tma<32>(tmx, tmdy, dw_t, g, slices, n_blocks, stream); break;
+    case 64: rc = launch_wgrad_tma<64>(tmx, tmdy, dw_t, g, slices, n_blocks, stream); break;
+    case 128: rc = launch_wgrad_tma<128>(tmx, tmdy, dw_t, g, slices, n_blocks, stream); break;
+    default: esb_set_error("%s: unsupported Cout %d", who, cout); return ESB_EINVAL;
   }
   if (rc != ESB_OK) return rc;
   ESB_CUDA_LAUNCH_CHECK("conv_tma_wgrad_kernel");
   return ESB_OK;
+}
+
+}  // namespace
+
+// dw_t (kh*kw*cin, cout) fp32, ZEROED BY THE CALLER: dW[co, ci, ky, kx] = dw_t[(ky*kw + kx)*cin + ci, co].
+// x (n,H,W,cin), dy (n,Ho,Wo,cout) bf16 NHWC; cin, cout in {16, 32, 64, 128, 256, 512, ...}.
+extern "C" int esb_conv2d_tma_wgrad(const void* x, const void* dy, float* dw_t, int n_img, int H, int W, int cin, int cout,
+                                    int kh, int kw, int stride, int pad, void* stream_) {
+  return conv_wgrad_any("esb_conv2d_tma_wgrad", x, dy, dw_t, n_img, 1, H, W, cin, cout, 1, kh, kw, stride, pad,
+                        (cudaStream_t)stream_);
+}
+
+// 3-D: dw_t (k*k*k*cin, cout) fp32 zeroed by the caller, row = ((kz*k + ky)*k + kx)*cin + ci; x (n,D,H,W,cin), dy NDHWC bf16.
+extern "C" int esb_conv3d_tma_wgrad(const void* x, const void* dy, float* dw_t, int n, int D, int H, int W, int cin, int cout, int k,
+                                    int stride, int pad, void* stream_) {
+  return conv_wgrad_any("esb_conv3d_tma_wgrad", x, dy, dw_t, n, D, H, W, cin, cout, k, k, k, stride, pad, (cudaStream_t)stream_);
 }

@@ -81,6 +81,84 @@ class _ConvOnly(nn.Module):
         return F.conv2d(x, self.conv.weight.to(x.dtype), self.conv.bias.to(x.dtype), 1, self.conv.padding)
 
 
+def _tma3d_ok(x, conv) -> bool:
+    """The dense 3-D stack runs on the library's TMA + tcgen05 kernels (csrc/conv_tma.cu, rank-5 tensor maps) when the
+    activations are bf16 on the GPU and the channel counts tile (16, 32, multiples of 64; outputs a power of two <= 256 or a
+    multiple of 256); anything else (fp32 parity arithmetic, toy widths) stays on the library convolution."""
+    import os
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and os.environ.get('ESB200_CONV3D', 'own') == 'own'):
+        return False
+    cin, cout = (conv.in_channels, conv.out_channels)
+
+    def ok(c):
+        return c in (16, 32) or (c >= 64 and c % 64 == 0)
+
+    def ok_out(c):
+        return (c <= 256 and c & (c - 1) == 0 and c >= 16) or (c > 256 and c % 256 == 0)
+
+    if isinstance(conv, nn.ConvTranspose3d):
+        return cin % 64 == 0 and (8 * cout) % 64 == 0 and tuple(conv.kernel_size) == (2, 2, 2) and tuple(conv.stride) == (2, 2, 2)
+    k, st, pd = conv.kernel_size, conv.stride, conv.padding
+    return (ok(cin) and ok(cout) and ok_out(cout) and ok_out(cin) and k[0] == k[1] == k[2] and k[0] in (1, 3)
+            and st[0] == st[1] == st[2] and st[0] in (1, 2) and pd[0] == pd[1] == pd[2])
+
+
+class _Conv3dTMA(torch.autograd.Function):
+    """nn.Conv3d (bias-free) on NDHWC bf16 volumes with the library's kernels, all three passes (esb_conv3d_tma_*)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, pad):
+        from . import _ffi
+        N, cin, D, H, W = x.shape
+        cout, _, k = w.shape[0], w.shape[1], w.shape[2]
+        if not x.is_contiguous(memory_format=torch.channels_last_3d):
+            x = x.contiguous(memory_format=torch.channels_last_3d)
+        w_odhwi = w.detach().permute(0, 2, 3, 4, 1).contiguous()
+        Do, Ho, Wo = ((D + 2 * pad - k) // stride + 1, (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1)
+        y = torch.empty((N, cout, Do, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last_3d)
+        _ffi.call('esb_conv3d_tma_fwd', x.data_ptr(), w_odhwi.data_ptr(), None, None, y.data_ptr(), N, D, H, W, cin, cout, k,
+                  stride, pad, 0, _ffi.stream())
+        ctx.save_for_backward(x, w_odhwi)
+        ctx.geom = (stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _ffi
+        x, w_odhwi = ctx.saved_tensors
+        stride, pad = ctx.geom
+        N, cin, D, H, W = x.shape
+        cout, k = w_odhwi.shape[0], w_odhwi.shape[1]
+        if not dy.is_contiguous(memory_format=torch.channels_last_3d):
+            dy = dy.contiguous(memory_format=torch.channels_last_3d)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _ffi.call('esb_conv3d_tma_dgrad', dy.data_ptr(), w_odhwi.data_ptr(), dx.data_ptr(), N, D, H, W, cin, cout, k, stride,
+                      pad, _ffi.stream())
+        if ctx.needs_input_grad[1]:
+            dw_t = torch.zeros((k * k * k * cin, cout), dtype=torch.float32, device=x.device)
+            _ffi.call('esb_conv3d_tma_wgrad', x.data_ptr(), dy.data_ptr(), dw_t.data_ptr(), N, D, H, W, cin, cout, k, stride, pad,
+                      _ffi.stream())
+            dw = dw_t.view(k, k, k, cin, cout).permute(4, 3, 0, 1, 2).to(x.dtype)
+        return dx, dw, None, None
+
+
+def _bn3d(bn, x, act=0, res=None):
+    """BatchNorm3d (+ residual) (+ ReLU) on an NDHWC volume through the row kernels of the sparse path (one segment)."""
+    if x.is_cuda and x.is_contiguous(memory_format=torch.channels_last_3d) and x.dtype in (torch.float32, torch.bfloat16) \
+            and x.shape[1] % 8 == 0:
+        N, C, D, H, W = x.shape
+        rows = x.permute(0, 2, 3, 4, 1).reshape(-1, C)
+        rres = res.contiguous(memory_format=torch.channels_last_3d).permute(0, 2, 3, 4, 1).reshape(-1, C) if res is not None else None
+        y = SP.batch_norm_rows(rows, bn, bn.training, act, rres)
+        return y.view(N, D, H, W, C).permute(0, 4, 1, 2, 3)
+    y = bn(x)
+    if res is not None:
+        y = y + res
+    return F.relu(y) if act == SP.ACT_RELU else y
+
+
 class ResModule(nn.Module):
 
     def __init__(self, in_channels, out_channels, stride=1):
@@ -97,25 +175,49 @@ class ResModule(nn.Module):
 
     def forward(self, x):
         identity = x
-        out = self.relu(self.norm1(_conv3d(self.conv1, x)))
-        out = self.norm2(_conv3d(self.conv2, out))
+        out = _bn3d(self.norm1, _conv3d(self.conv1, x), SP.ACT_RELU)
+        out = _conv3d(self.conv2, out)
         if self.stride != 1:
-            identity = self.downsample[1](_conv3d(self.downsample[0], x))
-        return self.relu(out + identity)
+            identity = _bn3d(self.downsample[1], _conv3d(self.downsample[0], x))
+        return _bn3d(self.norm2, out, SP.ACT_RELU, res=identity)          # relu(norm2(out) + identity), one pass
 
 
 def _conv3d(conv, x):
+    if _tma3d_ok(x, conv):
+        w = SP.weight_operand(conv.weight, x.dtype)
+        if isinstance(conv, nn.ConvTranspose3d):
+            # k2 s2 transpose = a dense GEMM (voxels, Cin) x (Cin, 8*Cout) on the tensor-core rows kernel, then the 2x2x2
+            # children interleave into the fine grid
+            N, cin, D, H, W = x.shape
+            cout = conv.out_channels
+            rows = x.contiguous(memory_format=torch.channels_last_3d).permute(0, 2, 3, 4, 1).reshape(-1, cin)
+            wm = w.permute(0, 2, 3, 4, 1).reshape(cin, 8 * cout)                # (ci | i, j, k, co)
+            y = SP.rows_gemm(rows, wm).view(N, D, H, W, 2, 2, 2, cout)
+            y = y.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(N, 2 * D, 2 * H, 2 * W, cout)
+            return y.permute(0, 4, 1, 2, 3)                                     # NCDHW view of NDHWC memory
+        return _Conv3dTMA.apply(x, w, conv.stride[0], conv.padding[0])
     if isinstance(conv, nn.ConvTranspose3d):
         return F.conv_transpose3d(x, conv.weight.to(x.dtype), None, conv.stride)
     return F.conv3d(x, conv.weight.to(x.dtype), None, conv.stride, conv.padding)
 
 
 class _Seq3d(nn.Sequential):
-    """Sequential whose convolutions run in the activation dtype (bf16) while parameters stay fp32 masters."""
+    """Sequential whose convolutions run in the activation dtype (bf16) while parameters stay fp32 masters; a BatchNorm3d
+    followed by a ReLU is one fused row-kernel pass."""
 
     def forward(self, x):
-        for m in self:
-            x = _conv3d(m, x) if isinstance(m, (nn.Conv3d, nn.ConvTranspose3d)) else m(x)
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, (nn.Conv3d, nn.ConvTranspose3d)):
+                x = _conv3d(m, x)
+            elif isinstance(m, nn.BatchNorm3d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+                x = _bn3d(m, x, SP.ACT_RELU)
+                i += 1
+            else:
+                x = m(x)
+            i += 1
         return x
 
 

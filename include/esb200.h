@@ -142,6 +142,15 @@ int esb_conv2d_tma_wgrad(const void* x, const void* dy, float* dw_t, int n_img, 
  * class of dx, stored through a tensor map that skips every other pixel; every dx element is written exactly once. */
 int esb_conv2d_tma_dgrad(const void* dy, const void* w_ohwi, void* dx, int n_img, int H, int W, int cin, int cout, int kh,
                          int kw, int stride, int pad, void* stream);
+/* The same three kernels on (n,D,H,W,C) volumes through rank-5 tensor maps: the dense Conv3d stack of the occupancy neck
+ * (embodiedscan/models/necks/imvoxel_neck.py:86-129; †upstream nn.Conv3d). x / y / dy NDHWC bf16, w_odhwi (cout,k,k,k,cin) bf16,
+ * dw_t (k*k*k*cin, cout) fp32 zeroed by the caller. */
+int esb_conv3d_tma_fwd(const void* x, const void* w_odhwi, const float* bias, const void* residual, void* y, int n, int D, int H,
+                       int W, int cin, int cout, int k, int stride, int pad, int relu, void* stream);
+int esb_conv3d_tma_dgrad(const void* dy, const void* w_odhwi, void* dx, int n, int D, int H, int W, int cin, int cout, int k,
+                         int stride, int pad, void* stream);
+int esb_conv3d_tma_wgrad(const void* x, const void* dy, float* dw_t, int n, int D, int H, int W, int cin, int cout, int k,
+                         int stride, int pad, void* stream);
 /* The 7x7/2 stem on the 3-channel image as a tcgen05 implicit GEMM with the im2col rows built in shared memory
  * (csrc/conv_tma.cu::stem7x7_tc_kernel). x (n_img,H,W,3) bf16 NHWC, w_ohwi (16,7,7,3) bf16, bias (16) fp32, y (n_img,Ho,Wo,16). */
 int esb_stem7x7_tc(const void* x, const void* w_ohwi, const float* bias, void* y, int n_img, int H, int W, int relu,

@@ -57,6 +57,42 @@ def run_stem(dev):
     print(json.dumps(dict(kind='bench_stem', us=1e3 * ms, gbs=(x.numel() + y.numel()) * 2 / ms / 1e6)), flush=True)
 
 
+def run_conv3d(dev):
+    """Rank-5 tensor maps: nn.Conv3d forward / dgrad (stride 1, 2) / wgrad and the k2 s2 transpose of the occupancy neck
+    through occupancy._conv3d, against torch fp32 on bf16-rounded operands."""
+    import torch.nn as nn
+    from embodiedscan_b200.occupancy import _conv3d
+    cases = [(64, 64, 3, 1, 1, (6, 10, 8), 2), (64, 128, 3, 2, 1, (6, 10, 8), 2), (128, 256, 1, 2, 0, (6, 10, 8), 1),
+             (256, 256, 3, 1, 1, (4, 5, 5), 1), (768, 256, 3, 1, 1, (4, 6, 5), 1), (128, 64, 2, 2, 0, (3, 5, 4), 2)]
+    for cin, cout, k, stride, pad, dhw, n in cases:
+        g = torch.Generator().manual_seed(cin + cout + k)
+        transpose = k == 2
+        conv = (nn.ConvTranspose3d(cin, cout, 2, 2, bias=False) if transpose else nn.Conv3d(cin, cout, k, stride, pad, bias=False))
+        with torch.no_grad():
+            conv.weight.copy_((torch.randn(conv.weight.shape, generator=g) / (cin * k ** 3) ** 0.5).bfloat16().float())
+        x = torch.randn(n, cin, *dhw, generator=g).bfloat16()
+        xr = x.float().requires_grad_(True)
+        ref = conv(xr)
+        go = torch.randn(ref.shape, generator=g).bfloat16()
+        ref.backward(go.float())
+        wref = conv.weight.grad.clone()
+        conv.weight.grad = None
+        convd = conv.to(dev)
+        xd = x.to(dev).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+        out = _conv3d(convd, xd)
+        out.backward(go.to(dev))
+        torch.cuda.synchronize()
+        res = dict(kind='conv3d', case=[cin, cout, k, stride, pad, list(dhw), n])
+        ok = tuple(out.shape) == tuple(ref.shape)
+        for name, a, b in (('fwd', out, ref), ('dgrad', xd.grad, xr.grad), ('wgrad', convd.weight.grad, wref)):
+            err = float((a.float().cpu() - b.detach()).abs().max())
+            tol = 1e-2 * max(float(b.detach().abs().max()), 1.0)
+            res[name] = err
+            ok = ok and err <= tol
+        res['ok'] = bool(ok)
+        print(json.dumps(res), flush=True)
+
+
 def run_case(case, dev):
     from embodiedscan_b200.backbones import conv2d_tma, conv2d_tma_dgrad, ohwi
     cin, cout, k, stride, pad, hw, n, with_res = case
@@ -167,6 +203,12 @@ def main():
         run_stem(dev)
     except Exception as e:  # noqa
         print(json.dumps(dict(kind='error', case='stem', ok=False, err=str(e)[:300])), flush=True)
+    if not only:
+        try:
+            run_conv3d(dev)
+        except Exception as e:  # noqa
+            import traceback
+            print(json.dumps(dict(kind='error', case='conv3d', ok=False, err=traceback.format_exc()[-400:])), flush=True)
     if '--bench' in sys.argv:
         bench(dev)
 

@@ -30,7 +30,17 @@ def _worker(rank, world, port, q):
     arena, red = optim.arena, optim.reducer
     batches = [synth_batch(10 + r, 1, n_views=2, H=240, W=320, n_points=2000, device=dev) for r in range(world)]
 
+    # the head normalises its losses by the mean over ranks of the positives per scan (fcaf3d_head.py:1183, dist_utils.py:9):
+    # the single-rank passes must use the normaliser of the distributed pass, not their own
+    head, store = model.bbox_head, {}
+    orig_reduce = head._reduce_mean
+
+    def recording(x):
+        store['n_pos'] = orig_reduce(x).clone()
+        return store['n_pos']
+
     def grads(b, reduce):
+        head._reduce_mean = recording if reduce else (lambda x: store['n_pos'].clone())
         arena.zero_grad()
         red.reset()
         red.enabled = reduce

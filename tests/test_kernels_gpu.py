@@ -553,7 +553,7 @@ def test_conv2d_tma_family_matches_torch():
     bad = [r for r in rows if not r.get('ok', True)]
     assert not bad, bad
     kinds = {r['kind'] for r in rows}
-    assert {'fwd', 'dgrad', 'wgrad', 'stem'} <= kinds, kinds
+    assert {'fwd', 'dgrad', 'wgrad', 'stem', 'conv3d'} <= kinds, kinds
 
 
 def test_spconv_tma_matches_cp_async_kernels():
