@@ -358,8 +358,9 @@ def main():
     ms_roof = r0.elapsed_time(r1)
     log('roofline pass done')
     barrier()
-    sample_at = {max(args.steps // 3, 0), max(2 * args.steps // 3, 0)}
-    _ffi.launch_counter.update(kernels=0, calls=0, by_name={})
+    # clocks are sampled (NVML, main thread) twice during the pre-roll — the same workload under the same load — and ONCE in
+    # the middle of the timed region: every NVML query was followed by a 60-140 ms stall of the next step
+    sample_at = {} if os.environ.get('ESB_BENCH_NOSAMPLE') == '1' else {max(args.steps // 2, 0)}
     prof_range = os.environ.get('ESB_CUDA_PROFILER_RANGE') == '1'    # for `ncu --profile-from-start off`
     if prof_range:
         torch.cuda.profiler.start()
@@ -368,22 +369,34 @@ def main():
     gc.freeze()        # setup objects (model, batches, profile records) leave the collector's working set
     # pre-roll: after an idle period (barrier, gc, event bookkeeping of the roofline pass) single steps stall for 40-400 ms
     # during roughly the next half second (seen at N = 1 and N = 2 alike, never later): run through it before timing
+    n_pre = max(3, min(args.steps, 20))
     pre_t = [time.perf_counter()]
-    for j in range(max(3, min(args.steps, 20))):
+    for j in range(n_pre):
         step(j)
+        if j in (n_pre // 3, 2 * n_pre // 3):
+            sampler.sample()
         pre_t.append(time.perf_counter())
     torch.cuda.synchronize()
     log('host ms per pre-roll step: ' + ' '.join(f'{1e3 * (b - a):.1f}' for a, b in zip(pre_t[:-1], pre_t[1:])))
+    if os.environ.get('ESB_BENCH_NOGC') == '1':
+        gc.disable()
+    gc0 = [g['collections'] for g in gc.get_stats()]
+    _ffi.launch_counter.update(kernels=0, calls=0, by_name={})
     host_t = [time.perf_counter()]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for j in range(args.steps):
         logs = step(args.warmup + j)
         if j in sample_at:
+            ts = time.perf_counter()
             sampler.sample()          # under load, inside the timed region
+            log(f'clock sample at timed step {j}: {1e3 * (time.perf_counter() - ts):.2f} ms')
         host_t.append(time.perf_counter())
     e1.record()
     barrier()
+    gc.enable()
+    log('gc collections during the timed region (gen0, gen1, gen2): ' +
+        ' '.join(str(b['collections'] - a) for a, b in zip(gc0, gc.get_stats())))
     log('host ms per timed step: ' + ' '.join(f'{1e3 * (b - a):.1f}' for a, b in zip(host_t[:-1], host_t[1:])))
     if prof_range:
         torch.cuda.profiler.stop()
