@@ -326,7 +326,7 @@ def main():
             for j in range(2):
                 step(j)
             torch.cuda.synchronize()
-        with open(args.torch_profile, 'w') as f:
+        with open(args.torch_profile + (f'.rank{rank}' if world > 1 else ''), 'w') as f:
             f.write(prof.key_averages().table(sort_by='cuda_time_total', row_limit=60, max_name_column_width=70))
             f.write('\n\n')
             f.write(prof.key_averages().table(sort_by='self_cpu_time_total', row_limit=40, max_name_column_width=70))
@@ -378,8 +378,8 @@ def main():
         pre_t.append(time.perf_counter())
     torch.cuda.synchronize()
     log('host ms per pre-roll step: ' + ' '.join(f'{1e3 * (b - a):.1f}' for a, b in zip(pre_t[:-1], pre_t[1:])))
-    if os.environ.get('ESB_BENCH_NOGC') == '1':
-        gc.disable()
+    if os.environ.get('ESB_BENCH_AUTOGC') == '1':     # A/B: the interpreter's automatic collector instead of the engine's schedule
+        gc.enable()
     gc0 = [g['collections'] for g in gc.get_stats()]
     _ffi.launch_counter.update(kernels=0, calls=0, by_name={})
     host_t = [time.perf_counter()]
@@ -394,7 +394,6 @@ def main():
         host_t.append(time.perf_counter())
     e1.record()
     barrier()
-    gc.enable()
     log('gc collections during the timed region (gen0, gen1, gen2): ' +
         ' '.join(str(b['collections'] - a) for a, b in zip(gc0, gc.get_stats())))
     log('host ms per timed step: ' + ' '.join(f'{1e3 * (b - a):.1f}' for a, b in zip(host_t[:-1], host_t[1:])))

@@ -24,3 +24,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _restore_collector():
+    """engine.OptimWrapper takes the cyclic collector over for the lifetime of a training job (gc_interval); a test session
+    builds many short-lived models, so every test hands the interpreter's automatic collection back and frees what it left."""
+    import gc
+    yield
+    gc.enable()
+    gc.collect()
