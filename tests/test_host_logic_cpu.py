@@ -272,3 +272,28 @@ def test_continuous_occupancy_view_prefix_painting_control_flow(monkeypatch):
     for i in range(n_prefix):
         assert float(fused[i, :C2d].min()) == float(fused[i, :C2d].max()) == float(i + 1)
     assert float(fused[:, C2d:].min()) == 1.0 and float(valid.min()) == 1.0
+
+
+def test_optim_wrapper_paramwise_lr_mult_and_gc_schedule():
+    """engine.OptimWrapper: mmengine `paramwise_cfg.custom_keys` becomes one per-element multiplier over the arena (longest key
+    wins), and the wrapper takes the cyclic collector over (automatic collection off, scheduled young-generation passes)."""
+    import gc
+    import torch
+    from embodiedscan_b200.engine import OptimWrapper
+    net = torch.nn.Sequential()
+    net.add_module('decoder', torch.nn.Linear(4, 4))
+    net.add_module('text_encoder', torch.nn.Linear(4, 2))
+    net.add_module('head', torch.nn.Linear(2, 2))
+    was = gc.isenabled()
+    try:
+        ow = OptimWrapper(net, paramwise_cfg=dict(custom_keys={'decoder': dict(lr_mult=0.1), 'text_encoder': dict(lr_mult=0.0),
+                                                               'decoder.bias': dict(lr_mult=0.5)}), gc_interval=7)
+        assert not gc.isenabled() and ow.gc_interval == 7
+        m = ow.optimizer.lr_mult
+        for p, o in zip(ow.arena.params, ow.arena.offsets):
+            name = {id(q): n for n, q in net.named_parameters()}[id(p)]
+            want = 0.5 if name == 'decoder.bias' else 0.1 if name.startswith('decoder') else 0.0 if name.startswith('text') else 1.0
+            assert torch.all(m[o:o + p.numel()] == want), (name, want)
+        assert OptimWrapper(net, gc_interval=None).optimizer.lr_mult is None
+    finally:
+        gc.enable() if was else gc.disable()
