@@ -30,7 +30,7 @@ import torch.nn.functional as F
 from . import sparse as SP
 from ._ffi import call, ptr, stream
 from .dense_heads import FCAF3DHeadRotMat
-from .detectors import SparseFeatureFusionSingleStage3DDetector, parse_losses
+from .detectors import SparseFeatureFusionSingleStage3DDetector, detach_log_vars, parse_losses
 from .fusion import pack_paint_metas, pack_projections, paint_points
 from .geometry import (bbox_to_corners, box3d_overlap, box_corners_container, chamfer_l1_src,
                        matrix_to_euler_angles_zxy, ortho_6d_2_mat, rotation_3d_in_euler)
@@ -829,7 +829,7 @@ class SparseFeatureFusion3DGrounder(nn.Module):
         data = self.data_preprocessor(data, True)
         loss, log_vars = parse_losses(self(**data, mode='loss'))
         optim_wrapper.update_params(loss)
-        return log_vars
+        return detach_log_vars(log_vars)
 
     @torch.no_grad()
     def val_step(self, data):

@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import sparse as SP
-from .detectors import parse_losses
+from .detectors import detach_log_vars, parse_losses
 from .fusion import pack_paint_metas, pack_projections, paint_float_points
 from .registry import MODELS, TASK_UTILS
 
@@ -496,7 +496,7 @@ class DenseFusionOccPredictor(nn.Module):
         data = self.data_preprocessor(data, True)
         loss, log_vars = parse_losses(self(**data, mode='loss'))
         optim_wrapper.update_params(loss)
-        return log_vars
+        return detach_log_vars(log_vars)
 
     @torch.no_grad()
     def val_step(self, data):
