@@ -122,8 +122,8 @@ class _BiasResAct(torch.autograd.Function):
 
 
 def conv2d_tc(x: torch.Tensor, w_ohwi: torch.Tensor, bias, res, relu: bool, kh: int, kw: int, stride: int, pad: int):
-    """EXPERIMENTAL (ESB200_CONV2D=tc): the folded conv + bias + residual + ReLU block in ONE tcgen05 implicit-GEMM
-    launch (csrc/conv2d_tc.cu). x (N,Cin,H,W) bf16 in channels_last memory; w_ohwi (Cout, r_pad) bf16 from
+    """The folded conv + bias + residual + ReLU block in ONE tcgen05 implicit-GEMM launch with a cp.async gather
+    (csrc/conv2d_tc.cu: the measured baseline of csrc/conv_tma.cu). x (N,Cin,H,W) bf16 in channels_last memory; w_ohwi (Cout, r_pad) bf16 from
     :func:`pack_ohwi`; bias (Cout,) fp32 or None; res like the output or None. Forward only (frozen / inference)."""
     from . import _ffi
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
@@ -211,7 +211,7 @@ def pack_ohwi(w: torch.Tensor) -> torch.Tensor:
 
 
 def conv2d_tc_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw, stride: int, pad: int) -> torch.Tensor:
-    """EXPERIMENTAL: dL/dx of ``F.conv2d(x, w, stride, pad)`` with the same kernel in transposed-gather mode.
+    """dL/dx of ``F.conv2d(x, w, stride, pad)`` with the same kernel in transposed-gather mode.
     dy (N,Cout,Ho,Wo) bf16 channels_last; w (Cout,Cin,kh,kw); returns dx (N,Cin,H,W) bf16 channels_last."""
     from . import _ffi
     assert dy.is_cuda and dy.dtype == torch.bfloat16 and dy.is_contiguous(memory_format=torch.channels_last)
@@ -229,7 +229,7 @@ def conv2d_tc_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw, stride: int, pad: 
 
 
 def conv2d_tc_wgrad(x: torch.Tensor, dy: torch.Tensor, w_shape, stride: int, pad: int) -> torch.Tensor:
-    """EXPERIMENTAL: dL/dw of ``F.conv2d(x, w, stride, pad)``; x (N,Cin,H,W), dy (N,Cout,Ho,Wo) bf16 channels_last ->
+    """dL/dw of ``F.conv2d(x, w, stride, pad)``; x (N,Cin,H,W), dy (N,Cout,Ho,Wo) bf16 channels_last ->
     (Cout,Cin,kh,kw) fp32 (split-K partial sums accumulate through fp32 atomics)."""
     from . import _ffi
     cout, cin, kh, kw = w_shape
@@ -239,26 +239,6 @@ def conv2d_tc_wgrad(x: torch.Tensor, dy: torch.Tensor, w_shape, stride: int, pad
     _ffi.call('esb_conv2d_tc_wgrad', x.data_ptr(), dy.data_ptr(), dw_t.data_ptr(), x.shape[0], x.shape[2], x.shape[3], cin,
               cout, kh, kw, stride, pad, _ffi.stream())
     return dw_t.view(kh, kw, cin, cout).permute(3, 2, 0, 1)
-
-
-class _Conv2dTC(torch.autograd.Function):
-    """EXPERIMENTAL (ESB200_CONV2D=tc): ``F.conv2d(x, w, None, stride, pad)`` for bf16 channels_last activations with all
-    three passes on the tcgen05 kernels of csrc/conv2d_tc.cu."""
-
-    @staticmethod
-    def forward(ctx, x, w, stride, pad):
-        ctx.save_for_backward(x, w)
-        ctx.geom = (stride, pad)
-        return conv2d_tc(x, pack_ohwi(w), None, None, False, w.shape[2], w.shape[3], stride, pad)
-
-    @staticmethod
-    def backward(ctx, dy):
-        x, w = ctx.saved_tensors
-        stride, pad = ctx.geom
-        dy = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        dx = conv2d_tc_dgrad(dy, w, x.shape[2:], stride, pad) if ctx.needs_input_grad[0] else None
-        dw = conv2d_tc_wgrad(x, dy, w.shape, stride, pad).to(w.dtype) if ctx.needs_input_grad[1] else None
-        return dx, dw, None, None
 
 
 class _ConvBlock2D(torch.autograd.Function):

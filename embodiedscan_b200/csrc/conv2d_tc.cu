@@ -3,8 +3,8 @@
 // embodiedscan/models/detectors/sparse_featfusion_single_stage.py:130-136) as an implicit GEMM with the frozen
 // BatchNorm folded into the weights and bias + residual + ReLU fused into the epilogue.
 //
-// STATUS: EXPERIMENTAL. Written after round 1's GPU budget was spent: it compiles for sm_100a and is reachable only
-// through ESB200_CONV2D=tc (backbones.py) and its own parity test; the measured path still calls cuDNN.
+// STATUS: validated on the B200 in round 2 (19/19 cases); superseded on the measured path by conv_tma.cu (TMA-fed), kept as its
+// measured cp.async baseline (wgrad: 2.5-4.5x slower than the TMA version) and as the dgrad for strides above 2.
 //
 // GEMM view: M = n_img*Ho*Wo output pixels, N = Cout, reduction R = kh*kw*Cin ordered (ky, kx, ci) — i.e. the weight
 // in OHWI (= PyTorch channels_last) layout IS the K-major B operand, row n = output channel, R contiguous, zero padded
