@@ -560,10 +560,17 @@ class ResNet(nn.Module):
         if entry is None or entry[0] != sig:
             if len(graphs) >= 4:
                 graphs.clear()
+            from . import _ffi
             shim = _GraphShim(self)
             sample = torch.empty_like(x).copy_(x)
+            k0 = _ffi.launch_counter['kernels']
             fn = torch.cuda.make_graphed_callables(shim, (sample, ), num_warmup_iters=3, allow_unused_input=True)
-            entry = graphs[key] = (sig, fn)
+            # kernels of one forward + backward pair of the branch (3 warm-up iterations + 1 capture ran through _ffi.call):
+            # a replay launches them without passing through Python, so the launch counter is advanced by hand below
+            per_pair = (_ffi.launch_counter['kernels'] - k0) // 4
+            entry = graphs[key] = (sig, fn, per_pair)
+        from . import _ffi
+        _ffi.launch_counter['kernels'] += entry[2]
         return entry[1](x)
 
     # checkpoint compatibility with mmdet / torchvision parameter names: a state-dict hook (not a `state_dict` override,

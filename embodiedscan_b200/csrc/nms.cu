@@ -110,6 +110,16 @@ __device__ float box_overlap_bev(const float* a, const float* b) {
 }
 
 __device__ __forceinline__ float iou_bev(const float* a, const float* b) {
+  // Disjoint bounding circles (plus 0.05 m, well beyond the 1e-2 containment margin of the clipping code) => no corner of one
+  // rectangle is inside or near the other and no edges cross: the clipped polygon is empty and the IoU is exactly 0, which is
+  // what the full computation returns. Skipping it here turns the greedy pass over scattered candidates from clipping-bound
+  // (24 ms per scan at 4000 x 284 candidates) into a distance test.
+  {
+    const float dx = a[0] - b[0], dy = a[1] - b[1];
+    const float ra = 0.5f * sqrtf(a[3] * a[3] + a[4] * a[4]), rb = 0.5f * sqrtf(b[3] * b[3] + b[4] * b[4]);
+    const float reach = ra + rb + 0.05f;
+    if (dx * dx + dy * dy > reach * reach) return 0.f;
+  }
   float sa = a[3] * a[4], sb = b[3] * b[4];
   float so = box_overlap_bev(a, b);
   return so / fmaxf(sa + sb - so, NMS_EPS);
