@@ -178,7 +178,7 @@ def cpu_baseline(cfg, variant_args, budget_s=30.0, backward=True, max_steps=None
     scan = synth_scan(0, device='cpu', **variant_args)
     tried = {}
     cores = min(nproc, 32)
-    if warmup > 0:
+    if warmup >= 2:        # two warm-up scans = the thread-count calibration (the in-bench cpu_baseline leg passes 1: no calibration)
         for c in sorted({min(nproc, 32), nproc}):
             torch.set_num_threads(c)
             t0 = time.perf_counter()
@@ -205,7 +205,7 @@ def cpu_baseline(cfg, variant_args, budget_s=30.0, backward=True, max_steps=None
 
 def cpu_baseline_subprocess(args, timeout_s=200):
     """Run the CPU port in a child process so a slow host cannot stall the GPU measurement."""
-    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2', '--warmup', '2',
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2', '--warmup', '1',
            '--views', str(args.views), '--height', str(args.height), '--width', str(args.width), '--points',
            str(args.points), '--variant', args.variant]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES='', RANK='0', WORLD_SIZE='1')
