@@ -70,6 +70,8 @@ def parse():
     ap.add_argument('--points', type=int, default=None)
     ap.add_argument('--variant', default='C2', choices=sorted(VARIANTS))
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--run-ahead', type=int, default=int(os.environ.get('ESB200_RUN_AHEAD', '0')),
+                    help='optimiser steps the host may queue ahead of the device (engine.OptimWrapper.max_run_ahead)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--torch-profile', default='', help='write a torch.profiler kernel table of 2 steps to this path')
@@ -287,7 +289,7 @@ def main():
         cfg = mv_grounding_config('C4')
         opt = dict(lr=5e-4, weight_decay=5e-4, max_norm=10.0)
     model = MODELS.build(dict(cfg, compute_dtype=dtype)).to(dev).train()
-    optim = OptimWrapper(model, **opt)
+    optim = OptimWrapper(model, max_run_ahead=args.run_ahead, **opt)
     broadcast_parameters(optim.arena)
 
     n_distinct = 2
@@ -504,7 +506,7 @@ def main():
            'config': {'workload': f'{args.variant}: train step, {args.batch} scans/GPU x {args.views} views '
                                   f'{args.height}x{args.width} RGB-D, {args.points} points/scan, {V["model"]}, AdamW + clip',
                       'global_batch': world * args.batch, 'parallelism': f'dp{world}',
-                      'row_order': os.environ.get('ESB200_ROW_ORDER', 'input'),
+                      'row_order': os.environ.get('ESB200_ROW_ORDER', 'input'), 'run_ahead': args.run_ahead,
                       'l2': 'per-step working set (340 MB fp32 weights + multi-GB activations) exceeds the 126 MB L2; '
                             f'{n_distinct} distinct input batches alternate; {n_distinct} untimed setup steps precede the W warm-up steps',
                       'loss': {k: float(v) for k, v in logs.items()}},
