@@ -70,7 +70,7 @@ def parse():
     ap.add_argument('--points', type=int, default=None)
     ap.add_argument('--variant', default='C2', choices=sorted(VARIANTS))
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--run-ahead', type=int, default=int(os.environ.get('ESB200_RUN_AHEAD', '0')),
+    ap.add_argument('--run-ahead', type=int, default=int(os.environ.get('ESB200_RUN_AHEAD', '1')),
                     help='optimiser steps the host may queue ahead of the device (engine.OptimWrapper.max_run_ahead)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
