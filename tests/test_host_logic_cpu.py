@@ -297,3 +297,17 @@ def test_optim_wrapper_paramwise_lr_mult_and_gc_schedule():
         assert OptimWrapper(net, gc_interval=None).optimizer.lr_mult is None
     finally:
         gc.enable() if was else gc.disable()
+
+
+def test_train_step_log_vars_carry_no_autograd_history():
+    """detectors.detach_log_vars: what `train_step` returns must not keep the finished step's graph (and through it the kernel
+    maps of the sparse-conv nodes) alive in the caller's hands."""
+    import torch
+    from embodiedscan_b200.detectors import detach_log_vars, parse_losses
+    w = torch.ones(3, requires_grad=True)
+    loss, log_vars = parse_losses({'loss_a': (w * 2).sum(), 'loss_b': [(w * 3).sum(), (w * 4).sum()], 'acc': torch.tensor(0.5)})
+    assert loss.requires_grad and log_vars['loss'].grad_fn is not None
+    out = detach_log_vars(log_vars)
+    assert set(out) == set(log_vars)
+    assert all(v.grad_fn is None and not v.requires_grad for v in out.values())
+    assert float(out['loss']) == float(loss) == 6 + 9 + 12
