@@ -44,6 +44,8 @@ SIGNATURES = {
     'esb_bias_act_fwd': ('ppppqiiip', 'i'),
     'esb_act_bwd': ('pppqiip', 'i'),
     'esb_gather2_rows': ('ppqpppqiip', 'i'),
+    'esb_head_split_fwd': ('pppqiiiifppppp', 'i'),
+    'esb_head_split_bwd': ('pppppqiiiifpppp', 'i'),
     'esb_conv2d_tc_fwd': ('ppppp' + 'iiiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tc_dgrad': ('ppp' + 'iiiiiiiiii' + 'p', 'i'),
     'esb_conv2d_tc_wgrad': ('ppp' + 'iiiiiiiii' + 'p', 'i'),

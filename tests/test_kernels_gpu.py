@@ -651,3 +651,45 @@ def test_flash_attention_tc_matches_softmax_attention():
     bad = [r for r in rows if not r.get('ok', True)]
     assert not bad, bad
     assert sum(r['kind'] == 'attn' for r in rows) >= 6
+
+
+def test_head_epilogue_kernel_matches_aten_chain():
+    """esb_head_split_fwd / _bwd against the slice / bias / Scale / exp / clamp / cat chain of fcaf3d_head.py:1116-1149 on the
+    same bf16 head-GEMM output: forward tensors bit-exact (same roundings), gradients to bf16 / fp32-sum tolerance; rows that
+    hit the clamp floor pass no gradient; N = 0 and a width that is not the model's."""
+    from embodiedscan_b200 import dense_heads as DH
+    torch.manual_seed(11)
+    for N, n_cls, n_reg, W in ((4099, 284, 12, 320), (37, 18, 12, 64), (0, 284, 12, 320)):
+        out = (torch.randn(N, W, device=_dev()) * 2).bfloat16()
+        if N:
+            out[: N // 3, n_cls + 1:n_cls + 7] -= 30.0         # exp(s x) < 1e-3: the clamp floor, zero gradient
+        bias = torch.randn(n_cls, device=_dev())
+        scale = torch.tensor(1.3, device=_dev())
+        g_cls = torch.randn(N, n_cls, device=_dev()).bfloat16()
+        g_ctr = torch.randn(N, 1, device=_dev())
+        g_box = torch.randn(N, n_reg, device=_dev())
+
+        o1, b1, s1 = out.clone().requires_grad_(True), bias.clone().requires_grad_(True), scale.clone().requires_grad_(True)
+        cls, ctr, box, score = DH._HeadSplit.apply(o1, b1, s1, n_cls, n_reg)
+        assert not score.requires_grad
+        (cls.float() * g_cls.float()).sum().add((ctr * g_ctr).sum()).add((box * g_box).sum()).backward()
+
+        o2, b2, s2 = out.clone().requires_grad_(True), bias.clone().requires_grad_(True), scale.clone().requires_grad_(True)
+        cls_r = o2[:, :n_cls] + b2.to(o2.dtype)
+        small = o2[:, n_cls:n_cls + 1 + n_reg].float()
+        ctr_r, reg = small[:, :1], small[:, 1:]
+        box_r = torch.cat((torch.exp(reg[:, :6] * s2).clamp(min=1e-3), reg[:, 6:]), 1)
+        (cls_r.float() * g_cls.float()).sum().add((ctr_r * g_ctr).sum()).add((box_r * g_box).sum()).backward()
+
+        assert cls.shape == (N, n_cls) and ctr.shape == (N, 1) and box.shape == (N, n_reg) and score.shape == (N, 1)
+        assert o1.grad.shape == (N, W)
+        if N == 0:
+            continue
+        assert torch.equal(cls, cls_r) and torch.equal(ctr, ctr_r)
+        _close(box, box_r, 1e-6, 'head epilogue bbox')
+        assert torch.equal(score, cls_r.max(1, keepdim=True).values.float())
+        assert float(o1.grad[:, n_cls + 1 + n_reg:].abs().max()) == 0.0
+        assert float(o1.grad[: N // 3, n_cls + 1:n_cls + 7].abs().max()) == 0.0
+        _close(o1.grad, o2.grad, 1e-2, 'head epilogue dout')
+        _close(b1.grad, b2.grad, 1e-2, 'head epilogue dbias')
+        _close(s1.grad, s2.grad, 1e-3, 'head epilogue dscale')
