@@ -165,7 +165,7 @@ def oracle_step(sd, cfg, scan, backward=True):
         total.backward()
         for v in sd.values():
             v.grad = None
-    return float(total)
+    return float(total.detach())
 
 
 def cpu_baseline(cfg, variant_args, budget_s=30.0, backward=True, max_steps=None, warmup=0):
